@@ -1,0 +1,482 @@
+// capi.cu -- extern "C" boundary of libgfpp.so (see include/gfpp.h for the contract).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cuda_runtime.h>
+
+#include "../../include/gfpp.h"
+#include "common.cuh"
+#include "head_kernel.cuh"
+#include "launch.cuh"
+#include "torso_kernel.cuh"
+
+namespace gfpp {
+// ops_kernels.cu
+cudaError_t launch_near_far(const float *, const float *, const float *, uint32_t, float, float *, float *, cudaStream_t);
+cudaError_t launch_march_rays(const MarchConst &, uint32_t, uint32_t, const int32_t *, const float *, const float *,
+                              const float *, const float *, float *, float *, float *, const float *, cudaStream_t);
+cudaError_t launch_composite_rays(uint32_t, uint32_t, float, int32_t *, float *, const float *, const float *,
+                                  const float *, float *, float *, float *, cudaStream_t);
+cudaError_t launch_grid_encode(const GridMeta &, const float *, const float *, float *, uint32_t, cudaStream_t);
+cudaError_t launch_sh_encode(const float *, float *, uint32_t, uint32_t, cudaStream_t);
+cudaError_t launch_freq_encode(const float *, uint32_t, uint32_t, uint32_t, float *, cudaStream_t);
+cudaError_t launch_occupancy_bounds(const uint8_t *, uint32_t, uint32_t, int *, cudaStream_t);
+}  // namespace gfpp
+
+using namespace gfpp;
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+bool g_profile = false;
+cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+// CK: a kernel launch (counted in gfpp_last_launch_count); CKN: any other runtime call
+#define CK(expr)                                                                      \
+    do {                                                                              \
+        cudaError_t e__ = (expr);                                                     \
+        if (e__ != cudaSuccess) return fail(GFPP_ERR_CUDA, #expr ": %s", cudaGetErrorString(e__)); \
+        ++g_launches;                                                                 \
+    } while (0)
+#define CKN(expr)                                                                     \
+    do {                                                                              \
+        cudaError_t e__ = (expr);                                                     \
+        if (e__ != cudaSuccess) return fail(GFPP_ERR_CUDA, #expr ": %s", cudaGetErrorString(e__)); \
+    } while (0)
+
+// Level constants exactly as the reference kernel derives them (gridencoder.cu:137-139, :66-84), computed once on
+// the host with the same libm calls as oracle/native_ops.c.
+int fill_grid_meta(GridMeta &gm, const int32_t *offsets, uint32_t D, uint32_t L, float S, uint32_t H,
+                   uint32_t gridtype, int align_corners, uint32_t interp) {
+    if (L == 0 || L > GFPP_MAX_LEVELS || (D != 2 && D != 3) || !offsets) return -1;
+    memset(&gm, 0, sizeof(gm));
+    gm.num_levels = L;
+    gm.dim = D;
+    gm.interp = interp;
+    gm.align_off = align_corners ? 0.0f : 0.5f;
+    for (uint32_t l = 0; l < L; ++l) {
+        const float scale = exp2f((float)l * S) * (float)H - 1.0f;
+        const uint32_t res = (uint32_t)ceil((double)scale) + 1;
+        const uint32_t hs = (uint32_t)(offsets[l + 1] - offsets[l]);
+        const uint32_t step = align_corners ? res : res + 1;
+        gm.scale[l] = scale;
+        gm.offset[l] = (uint32_t)offsets[l];
+        gm.hsize[l] = hs;
+        uint32_t stride = 1;
+        uint32_t mul[3] = {0, 0, 0};
+        for (uint32_t d = 0; d < D && stride <= hs; ++d) {
+            mul[d] = stride;
+            stride *= step;  // uint32 wrap on purpose, as in the reference
+        }
+        if (mul[0] != 1) return -1;  // hashmap_size 0
+        gm.mul1[l] = mul[1];
+        gm.mul2[l] = mul[2];
+        gm.hashed[l] = (gridtype == 0 && stride > hs) ? 1u : 0u;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- packed model
+constexpr int kChunkK[HEAD_NCHUNK] = {48, 48, 64, 64, 64, 64, 64, 64, 64, 72, 72};
+
+struct ModelHost {
+    uint32_t magic;
+    int has_torso;
+    GridMeta pos_gm, amb_gm, tor_gm;
+    const float2 *pos_tab, *amb_tab, *tor_tab;
+    const uint8_t *bitfield;
+    const float *density_grid_torso;
+    const float *torso_def0_src, *torso_can0_src, *torso_code;  // originals (per-frame bias fold reads them)
+    uint32_t torso_code_dim;
+    // into packed
+    const float *wide, *narrow;
+    const float *wd0, *wd1, *wd2, *wc0, *wc1, *wc2;
+    const int *occ_bounds;
+    int chunk_off[HEAD_NCHUNK];
+    float aabb[6];
+    float bound, min_near, density_scale, density_thresh_torso, torso_shrink;
+    uint32_t cascade, grid_size;
+    int use_occ_box;
+};
+static_assert(sizeof(ModelHost) <= sizeof(gfpp_model), "gfpp_model opaque storage too small");
+constexpr uint32_t kMagic = 0x67667070u;  // "gfpp"
+
+struct PackedLayout {
+    size_t wide, narrow, wd0, wd1, wd2, wc0, wc1, wc2, occ, total;
+};
+
+PackedLayout packed_layout() {
+    PackedLayout L;
+    size_t o = 0;
+    auto take = [&](size_t floats) { size_t r = o; o += (floats * 4 + 255) / 256 * 256; return r; };
+    size_t wide = 0;
+    for (int c = 0; c < HEAD_NCHUNK; ++c) wide += (size_t)kChunkK[c] * 128;
+    L.wide = take(wide);
+    L.narrow = take(8 * 128);
+    L.wd0 = take(44 * 64);
+    L.wd1 = take(64 * 64);
+    L.wd2 = take(2 * 64);
+    L.wc0 = take(76 * 32);
+    L.wc1 = take(32 * 32);
+    L.wc2 = take(4 * 32);
+    L.occ = take(8);
+    L.total = o;
+    return L;
+}
+
+struct WorkLayout {
+    size_t image, rays_t, wsum, depth, survivors, zero_begin, hist, counters, B_total, valid, pcount, zero_end, bias_def,
+        bias_can, total;
+};
+
+WorkLayout work_layout(uint32_t F, uint32_t N, uint32_t max_steps) {
+    WorkLayout W;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
+    const size_t FN = (size_t)F * N;
+    W.image = take(FN * 3 * 4);
+    W.rays_t = take(FN * 4);
+    W.wsum = take(FN * 4);
+    W.depth = take(FN * 4);
+    W.survivors = take(FN * 4);
+    W.zero_begin = o;
+    W.hist = take((size_t)F * (max_steps + 2) * 4);
+    W.counters = take(16 * 4);
+    W.B_total = take((size_t)F * 4);
+    W.valid = take((size_t)F * 4);
+    W.pcount = take((size_t)F * 4);
+    W.zero_end = o;
+    W.bias_def = take((size_t)F * 64 * 4);
+    W.bias_can = take((size_t)F * 32 * 4);
+    W.total = o;
+    return W;
+}
+
+__global__ void k_init_bounds(int *b) {
+    if (threadIdx.x < 3) b[threadIdx.x] = INT_MAX;
+    else if (threadIdx.x < 6) b[threadIdx.x] = -1;
+}
+
+__global__ void k_write_stats(const int *B_total, const int *n_survivors, const int *valid, const int *pcount, int F,
+                              int32_t *stats) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    stats[4 * f] = B_total[f];
+    stats[4 * f + 1] = *n_survivors;
+    stats[4 * f + 2] = valid[f];
+    stats[4 * f + 3] = pcount[f];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *gfpp_last_error(void) { return g_err; }
+int gfpp_version(void) { return 100; }
+int gfpp_last_launch_count(void) { return g_launches; }
+
+int gfpp_profile_enable(int on) {
+    if (on && !g_ev[0]) {
+        for (int i = 0; i < 4; ++i)
+            if (cudaEventCreate(&g_ev[i]) != cudaSuccess) return fail(GFPP_ERR_CUDA, "cudaEventCreate failed%s");
+    }
+    g_profile = on != 0;
+    return GFPP_OK;
+}
+
+int gfpp_profile_read(float ms[3]) {
+    if (!g_profile || !g_ev[0] || !ms) return fail(GFPP_ERR_INVALID, "profile_read: profiling is not enabled%s");
+    CKN(cudaEventSynchronize(g_ev[3]));
+    for (int i = 0; i < 3; ++i) CKN(cudaEventElapsedTime(&ms[i], g_ev[i], g_ev[i + 1]));
+    return GFPP_OK;
+}
+
+int gfpp_check_device(void) {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess)
+        return fail(GFPP_ERR_CUDA, "no CUDA device%s");
+    if (p.major != 10) {
+        snprintf(g_err, sizeof(g_err), "libgfpp is built for sm_100a only; device is sm_%d%d", p.major, p.minor);
+        return GFPP_ERR_UNSUPPORTED;
+    }
+    return GFPP_OK;
+}
+
+// ------------------------------------------------------------------ (A) per-op mirror
+int gfpp_near_far_from_aabb(const float *rays_o, const float *rays_d, const float *aabb, uint32_t N, float min_near,
+                            float *nears, float *fars, void *stream) {
+    if (!rays_o || !rays_d || !aabb || !nears || !fars) return fail(GFPP_ERR_INVALID, "near_far_from_aabb: null pointer%s");
+    g_launches = 0;
+    CK(launch_near_far(rays_o, rays_d, aabb, N, min_near, nears, fars, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t,
+                    const float *rays_o, const float *rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
+                    uint32_t H, const uint8_t *grid, const float *nears, const float *fars, float *xyzs, float *dirs,
+                    float *deltas, const float *noises, void *stream) {
+    (void)nears;
+    if (!rays_alive || !rays_t || !rays_o || !rays_d || !grid || !fars || !xyzs || !dirs || !deltas || !noises)
+        return fail(GFPP_ERR_INVALID, "march_rays: null pointer%s");
+    if (C < 1 || C > 8 || H < 1 || H > 1024 || max_steps < 1) return fail(GFPP_ERR_INVALID, "march_rays: bad C/H/max_steps%s");
+    MarchConst mc;
+    march_const_init(mc, bound, dt_gamma, max_steps, C, H, grid);
+    g_launches = 0;
+    CK(launch_march_rays(mc, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, fars, xyzs, dirs, deltas, noises,
+                         (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive, float *rays_t,
+                        const float *sigmas, const float *rgbs, const float *deltas, float *weights_sum, float *depth,
+                        float *image, void *stream) {
+    if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image)
+        return fail(GFPP_ERR_INVALID, "composite_rays: null pointer%s");
+    g_launches = 0;
+    CK(launch_composite_rays(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth,
+                             image, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_grid_encode_forward(const float *inputs, const float *embeddings, const int32_t *offsets_host, float *outputs,
+                             uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                             int align_corners, uint32_t interp, void *stream) {
+    if (!inputs || !embeddings || !offsets_host || !outputs) return fail(GFPP_ERR_INVALID, "grid_encode_forward: null pointer%s");
+    // the reference throws std::runtime_error for unsupported C / D (gridencoder.cu:380, 397)
+    if (C != 2) return fail(GFPP_ERR_UNSUPPORTED, "GridEncoding: this build supports C == 2 only%s");
+    GridMeta gm;
+    if (fill_grid_meta(gm, offsets_host, D, L, S, H, gridtype, align_corners, interp) != 0)
+        return fail(GFPP_ERR_UNSUPPORTED, "GridEncoding: D must be 2 or 3 and L <= 16%s");
+    g_launches = 0;
+    CK(launch_grid_encode(gm, inputs, embeddings, outputs, B, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_sh_encode_forward(const float *inputs, float *outputs, uint32_t B, uint32_t D, uint32_t degree, void *stream) {
+    if (!inputs || !outputs) return fail(GFPP_ERR_INVALID, "sh_encode_forward: null pointer%s");
+    if (D != 3 || degree < 1 || degree > 4) return fail(GFPP_ERR_UNSUPPORTED, "SH encoder: D must be 3 and degree in 1..4%s");
+    g_launches = 0;
+    CK(launch_sh_encode(inputs, outputs, B, degree, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_freq_encode_forward(const float *inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C, float *outputs,
+                             void *stream) {
+    if (!inputs || !outputs) return fail(GFPP_ERR_INVALID, "freq_encode_forward: null pointer%s");
+    if (C != D + 2 * D * deg) return fail(GFPP_ERR_INVALID, "freq_encode_forward: C != D + 2*D*deg%s");
+    g_launches = 0;
+    CK(launch_freq_encode(inputs, B, D, C, outputs, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+// ------------------------------------------------------------------ (B) fused renderer
+size_t gfpp_model_packed_bytes(const gfpp_model_desc *desc) {
+    (void)desc;
+    return packed_layout().total;
+}
+
+int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes, gfpp_model *model, void *stream) {
+    if (!d || !packed || !model) return fail(GFPP_ERR_INVALID, "model_pack: null pointer%s");
+    const PackedLayout L = packed_layout();
+    if (packed_bytes < L.total) return fail(GFPP_ERR_WORKSPACE, "model_pack: packed buffer too small%s");
+    if (d->cond_dim != 64 || d->ind_dim > 16) return fail(GFPP_ERR_UNSUPPORTED, "model_pack: cond_dim must be 64, ind_dim <= 16%s");
+    if (d->cascade < 1 || d->cascade > 8 || d->grid_size < 8 || d->grid_size > 1024)
+        return fail(GFPP_ERR_UNSUPPORTED, "model_pack: cascade/grid_size out of range%s");
+    for (int i = 0; i < 3; ++i)
+        if (!d->ambient_w[i] || !d->sigma_w[i]) return fail(GFPP_ERR_INVALID, "model_pack: null weight%s");
+    if (!d->color_w[0] || !d->color_w[1] || !d->density_bitfield) return fail(GFPP_ERR_INVALID, "model_pack: null weight%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    ModelHost m;
+    memset(&m, 0, sizeof(m));
+    m.magic = kMagic;
+    const gfpp_grid_desc *gd[3] = {&d->position_grid, &d->ambient_grid, &d->torso_grid};
+    GridMeta *gm[3] = {&m.pos_gm, &m.amb_gm, &m.tor_gm};
+    for (int i = 0; i < (d->has_torso ? 3 : 2); ++i) {
+        if (!gd[i]->embeddings) return fail(GFPP_ERR_INVALID, "model_pack: null grid table%s");
+        if (gd[i]->num_levels != 16)
+            return fail(GFPP_ERR_UNSUPPORTED, "model_pack: grids must have 16 levels x 2 features%s");
+        if (fill_grid_meta(*gm[i], gd[i]->offsets_host, gd[i]->input_dim, gd[i]->num_levels, gd[i]->log2_per_level_scale,
+                           gd[i]->base_resolution, gd[i]->gridtype, gd[i]->align_corners, gd[i]->interp) != 0)
+            return fail(GFPP_ERR_UNSUPPORTED, "model_pack: unsupported grid layout%s");
+    }
+    if (m.pos_gm.dim != 3) return fail(GFPP_ERR_UNSUPPORTED, "model_pack: position grid must be 3-D%s");
+    if (d->has_torso && m.tor_gm.dim != 2) return fail(GFPP_ERR_UNSUPPORTED, "model_pack: torso grid must be 2-D%s");
+    m.pos_tab = (const float2 *)d->position_grid.embeddings;
+    m.amb_tab = (const float2 *)d->ambient_grid.embeddings;
+    m.tor_tab = d->has_torso ? (const float2 *)d->torso_grid.embeddings : nullptr;
+    m.bitfield = d->density_bitfield;
+    memcpy(m.aabb, d->aabb, sizeof(m.aabb));
+    m.bound = d->bound;
+    m.min_near = d->min_near;
+    m.density_scale = d->density_scale;
+    m.cascade = d->cascade;
+    m.grid_size = d->grid_size;
+    const float cube = d->bound;
+    m.use_occ_box = (d->cascade == 1 && d->aabb[0] >= -cube && d->aabb[1] >= -cube && d->aabb[2] >= -cube &&
+                     d->aabb[3] <= cube && d->aabb[4] <= cube && d->aabb[5] <= cube) ? 1 : 0;
+
+    char *base = (char *)packed;
+    float *wide = (float *)(base + L.wide), *narrow = (float *)(base + L.narrow);
+    g_launches = 0;
+    // stream order of the wide chunks (k-rows of the transposed weights): ambient L0 (96 = 48+48), ambient L1 (64+64),
+    // sigma L0 (64), sigma L1 (64+64), sigma L2 geo rows 1..128 (64+64), color L0 columns 0..143 (72+72)
+    struct Src { const float *w; int ld, row0, col0; };
+    const int amb_dim = (int)m.amb_gm.dim;
+    const int col0_in = 16 + 128 + (int)d->ind_dim;
+    const Src src[HEAD_NCHUNK] = {
+        {d->ambient_w[0], 96, 0, 0},  {d->ambient_w[0], 96, 0, 48}, {d->ambient_w[1], 128, 0, 0}, {d->ambient_w[1], 128, 0, 64},
+        {d->sigma_w[0], 64, 0, 0},    {d->sigma_w[1], 128, 0, 0},   {d->sigma_w[1], 128, 0, 64},  {d->sigma_w[2], 128, 1, 0},
+        {d->sigma_w[2], 128, 1, 64},  {d->color_w[0], col0_in, 0, 0}, {d->color_w[0], col0_in, 0, 72}};
+    int off = 0;
+    for (int c = 0; c < HEAD_NCHUNK; ++c) {
+        m.chunk_off[c] = off;
+        CK(launch_pack_kmajor(src[c].w, src[c].ld, src[c].row0, src[c].col0, 128, kChunkK[c], kChunkK[c], wide + off, st));
+        off += kChunkK[c] * 128;
+    }
+    CKN(cudaMemsetAsync(narrow, 0, 8 * 128 * 4, st));
+    CK(launch_pack_rows(d->ambient_w[2], 128, 0, amb_dim, 128, 128, narrow, st));            // rows 0..2
+    CK(launch_pack_rows(d->sigma_w[2], 128, 0, 1, 128, 128, narrow + 3 * 128, st));           // row 3: sigma
+    CK(launch_pack_rows(d->color_w[1], 128, 0, 3, 128, 128, narrow + 4 * 128, st));           // rows 4..6
+    if (d->ind_dim > 0)
+        CK(launch_fold_bias(d->color_w[0], col0_in, 144, (int)d->ind_dim, d->individual_code, 128, narrow + 7 * 128, st));
+    m.wide = wide;
+    m.narrow = narrow;
+
+    int *occ = (int *)(base + L.occ);
+    k_init_bounds<<<1, 32, 0, st>>>(occ);
+    CK(cudaGetLastError());
+    const uint32_t H3 = d->grid_size * d->grid_size * d->grid_size;
+    CK(launch_occupancy_bounds(d->density_bitfield, d->cascade * H3 / 8, H3, occ, st));
+    m.occ_bounds = occ;
+
+    m.has_torso = d->has_torso;
+    if (d->has_torso) {
+        for (int i = 0; i < 3; ++i)
+            if (!d->torso_deform_w[i] || !d->torso_canon_w[i]) return fail(GFPP_ERR_INVALID, "model_pack: null torso weight%s");
+        if (!d->density_grid_torso) return fail(GFPP_ERR_INVALID, "model_pack: null density_grid_torso%s");
+        if (d->torso_code_dim > 10) return fail(GFPP_ERR_UNSUPPORTED, "model_pack: torso_code_dim <= 10%s");
+        const int din = 42 + 54 + (int)d->torso_code_dim;
+        float *wd0 = (float *)(base + L.wd0), *wd1 = (float *)(base + L.wd1), *wd2 = (float *)(base + L.wd2);
+        float *wc0 = (float *)(base + L.wc0), *wc1 = (float *)(base + L.wc1), *wc2 = (float *)(base + L.wc2);
+        CK(launch_pack_kmajor(d->torso_deform_w[0], din, 0, 0, 64, 42, 44, wd0, st));
+        CK(launch_pack_kmajor(d->torso_deform_w[1], 64, 0, 0, 64, 64, 64, wd1, st));
+        CK(launch_pack_rows(d->torso_deform_w[2], 64, 0, 2, 64, 64, wd2, st));
+        CK(launch_pack_kmajor(d->torso_canon_w[0], 32 + din, 0, 0, 32, 74, 76, wc0, st));
+        CK(launch_pack_kmajor(d->torso_canon_w[1], 32, 0, 0, 32, 32, 32, wc1, st));
+        CK(launch_pack_rows(d->torso_canon_w[2], 32, 0, 4, 32, 32, wc2, st));
+        m.wd0 = wd0; m.wd1 = wd1; m.wd2 = wd2; m.wc0 = wc0; m.wc1 = wc1; m.wc2 = wc2;
+        m.torso_def0_src = d->torso_deform_w[0];
+        m.torso_can0_src = d->torso_canon_w[0];
+        m.torso_code = d->torso_code;
+        m.torso_code_dim = d->torso_code_dim;
+        m.density_grid_torso = d->density_grid_torso;
+        m.density_thresh_torso = d->density_thresh_torso;
+        m.torso_shrink = d->torso_shrink;
+    }
+    memset(model, 0, sizeof(*model));
+    memcpy(model, &m, sizeof(m));
+    return GFPP_OK;
+}
+
+size_t gfpp_render_workspace_bytes(uint32_t n_frames, uint32_t n_rays, uint32_t max_steps) {
+    return work_layout(n_frames, n_rays, max_steps).total;
+}
+
+int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfpp_outputs *out, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+    if (!model || !fr || !out || !workspace) return fail(GFPP_ERR_INVALID, "render_frames: null pointer%s");
+    ModelHost m;
+    memcpy(&m, model, sizeof(m));
+    if (m.magic != kMagic) return fail(GFPP_ERR_INVALID, "render_frames: model handle not initialised by gfpp_model_pack%s");
+    if (!out->rgb_map || !fr->cond_feat) return fail(GFPP_ERR_INVALID, "render_frames: rgb_map and cond_feat are required%s");
+    if (fr->n_frames == 0 || fr->n_rays == 0) return fail(GFPP_ERR_INVALID, "render_frames: empty clip%s");
+    if ((uint64_t)fr->n_frames * fr->n_rays >= (1ull << 31)) return fail(GFPP_ERR_UNSUPPORTED, "render_frames: F*N must be < 2^31%s");
+    if (fr->max_steps < 1 || fr->max_steps > 4096) return fail(GFPP_ERR_UNSUPPORTED, "render_frames: max_steps must be in 1..4096%s");
+    if ((fr->rays_o == nullptr) != (fr->rays_d == nullptr)) return fail(GFPP_ERR_INVALID, "render_frames: rays_o and rays_d go together%s");
+    if (!fr->rays_o && (!fr->poses_c2w || fr->img_w == 0 || fr->img_h * fr->img_w != fr->n_rays))
+        return fail(GFPP_ERR_INVALID, "render_frames: need rays or (poses_c2w, img_h*img_w == n_rays)%s");
+    if (m.has_torso && (!fr->torso_pose6 || !fr->bg_coords)) return fail(GFPP_ERR_INVALID, "render_frames: torso model needs torso_pose6 and bg_coords%s");
+    const WorkLayout W = work_layout(fr->n_frames, fr->n_rays, fr->max_steps);
+    if (workspace_bytes < W.total) return fail(GFPP_ERR_WORKSPACE, "render_frames: workspace too small%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    g_launches = 0;
+    CKN(cudaMemsetAsync(ws + W.zero_begin, 0, W.zero_end - W.zero_begin, st));
+
+    HeadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pos_gm = m.pos_gm; a.amb_gm = m.amb_gm;
+    a.pos_tab = m.pos_tab; a.amb_tab = m.amb_tab;
+    a.wide = m.wide; a.narrow = m.narrow;
+    for (int c = 0; c < HEAD_NCHUNK; ++c) { a.chunk_off[c] = m.chunk_off[c]; a.chunk_k[c] = kChunkK[c]; }
+    march_const_init(a.mc, m.bound, fr->dt_gamma, fr->max_steps, m.cascade, m.grid_size, m.bitfield);
+    a.occ_bounds = m.occ_bounds;
+    memcpy(a.aabb, m.aabb, sizeof(a.aabb));
+    a.min_near = m.min_near; a.density_scale = m.density_scale;
+    a.use_occ_box = m.use_occ_box;
+    a.n_frames = (int)fr->n_frames; a.n_rays = (int)fr->n_rays;
+    a.rays_o = fr->rays_o; a.rays_d = fr->rays_d; a.poses = fr->poses_c2w;
+    a.fx = fr->fx; a.fy = fr->fy; a.cx = fr->cx; a.cy = fr->cy; a.img_w = (int)fr->img_w;
+    a.cond_feat = fr->cond_feat;
+    a.max_steps = (int)fr->max_steps; a.T_thresh = fr->T_thresh;
+    a.image = (float *)(ws + W.image);
+    a.wsum = out->weights_sum ? out->weights_sum : (float *)(ws + W.wsum);
+    a.depth = out->depth_map ? out->depth_map : (float *)(ws + W.depth);
+    a.rays_t = (float *)(ws + W.rays_t);
+    a.hist = (int *)(ws + W.hist);
+    a.survivors = (int *)(ws + W.survivors);
+    int *counters = (int *)(ws + W.counters);
+    a.n_survivors = counters + 2;
+    a.B_total = (int *)(ws + W.B_total);
+    a.valid_samples = (int *)(ws + W.valid);
+
+    TorsoArgs t;
+    memset(&t, 0, sizeof(t));
+    t.has_torso = m.has_torso;
+    t.n_frames = a.n_frames; t.n_rays = a.n_rays;
+    t.image = a.image; t.wsum = a.wsum;
+    t.rgb_map = out->rgb_map;
+    t.bg_color = fr->bg_color;
+    t.P_count = (int *)(ws + W.pcount);
+    if (m.has_torso) {
+        t.tor_gm = m.tor_gm; t.tor_tab = m.tor_tab;
+        t.w_def0 = m.wd0; t.w_def1 = m.wd1; t.w_def2 = m.wd2; t.w_can0 = m.wc0; t.w_can1 = m.wc1; t.w_can2 = m.wc2;
+        t.bias_def = (float *)(ws + W.bias_def); t.bias_can = (float *)(ws + W.bias_can);
+        t.pose6 = fr->torso_pose6;
+        t.density_grid_torso = m.density_grid_torso; t.grid_size = (int)m.grid_size;
+        t.density_thresh_torso = m.density_thresh_torso; t.torso_shrink = m.torso_shrink;
+        t.bg_coords = fr->bg_coords;
+        t.torso_alpha = out->torso_alpha_map; t.torso_rgb = out->torso_rgb_map; t.deform = out->torso_deform;
+        CK(launch_torso_frame_bias(t, m.torso_def0_src, m.torso_can0_src, m.torso_code, (int)m.torso_code_dim,
+                                   (float *)(ws + W.bias_def), (float *)(ws + W.bias_can), st));
+    }
+
+    a.pass = 1;
+    a.cursor = counters + 0;
+    if (g_profile) CKN(cudaEventRecord(g_ev[0], st));
+    CK(launch_head(a, a.n_frames * a.n_rays, st));
+    if (g_profile) CKN(cudaEventRecord(g_ev[1], st));
+    CK(launch_schedule(a.hist, a.n_frames, a.n_rays, a.max_steps, a.B_total, st));
+    a.pass = 2;
+    a.cursor = counters + 1;
+    CK(launch_head(a, -1, st));
+    if (g_profile) CKN(cudaEventRecord(g_ev[2], st));
+    CK(launch_epilogue(t, st));
+    if (g_profile) CKN(cudaEventRecord(g_ev[3], st));
+    if (out->stats) {
+        k_write_stats<<<(a.n_frames + 63) / 64, 64, 0, st>>>(a.B_total, a.n_survivors, a.valid_samples, t.P_count,
+                                                             a.n_frames, out->stats);
+        CK(cudaGetLastError());
+    }
+    return GFPP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,265 @@
+// common.cuh -- shared device helpers of libgfpp (sm_100a).
+//
+// The ray-march helpers make DISCRETE decisions (cell index, occupancy bit, "t < far"), so their fp32
+// arithmetic is written with explicit round-to-nearest intrinsics (no FMA contraction) in exactly the
+// evaluation order of the reference kernel (modules/radnerfs/raymarching/src/raymarching.cu:857-927,
+// helpers :19-81) and of its CPU restatement oracle/native_ops.c.  See SURVEY.md section 7, H2.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#define GFPP_MAX_LEVELS 16
+
+namespace gfpp {
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(hi, fmaxf(lo, v)); }
+
+// 10-bit-per-axis Morton interleave (raymarching.cu:57-72)
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t morton3(uint32_t x, uint32_t y, uint32_t z) {
+    return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Marching constants shared by the per-op kernel and the fused renderer.
+struct MarchConst {
+    float bound, dt_gamma, dt_min, dt_max, rH, H3, Hm1, fC, fH;
+    uint32_t C, H;
+    const uint8_t *bits;
+    // tight cell-space bounds of the occupied voxels of cascade 0..C-1 (inclusive); cells outside are
+    // known empty, so their bit need not be read.  lo > hi means "no bounds available: always read".
+    int bb_lo[3], bb_hi[3];
+};
+
+__host__ __device__ inline void march_const_init(MarchConst &mc, float bound, float dt_gamma, uint32_t max_steps,
+                                                 uint32_t C, uint32_t H, const uint8_t *bits) {
+    mc.bound = bound;
+    mc.dt_gamma = dt_gamma;
+    const float sqrt3 = 1.7320508075688772f;
+    // raymarching.cu:866-867
+    mc.dt_max = 2 * sqrt3 * (float)(1 << (C - 1)) / (float)H;
+    mc.dt_min = fminf(mc.dt_max, 2 * sqrt3 / (float)max_steps);
+    mc.rH = 1.0f / (float)H;
+    mc.H3 = (float)(H * H * H);
+    mc.Hm1 = (float)(H - 1);
+    mc.fC = (float)C;
+    mc.fH = (float)H;
+    mc.C = C;
+    mc.H = H;
+    mc.bits = bits;
+    mc.bb_lo[0] = mc.bb_lo[1] = mc.bb_lo[2] = 1;
+    mc.bb_hi[0] = mc.bb_hi[1] = mc.bb_hi[2] = 0;
+}
+
+struct RayGeom {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+};
+
+__device__ __forceinline__ void ray_geom_init(RayGeom &g, float ox, float oy, float oz, float dx, float dy, float dz) {
+    g.ox = ox; g.oy = oy; g.oz = oz;
+    g.dx = dx; g.dy = dy; g.dz = dz;
+    g.rdx = __fdiv_rn(1.0f, dx);
+    g.rdy = __fdiv_rn(1.0f, dy);
+    g.rdz = __fdiv_rn(1.0f, dz);
+}
+
+// slab test (raymarching.cu:91-145).  Returns near/far; a miss sets both to FLT_MAX.
+__device__ __forceinline__ void near_far(const RayGeom &g, const float *aabb, float min_near, float &near, float &far) {
+    float tn = __fmul_rn(__fsub_rn(aabb[0], g.ox), g.rdx), tf = __fmul_rn(__fsub_rn(aabb[3], g.ox), g.rdx);
+    if (tn > tf) { float s = tn; tn = tf; tf = s; }
+    float tny = __fmul_rn(__fsub_rn(aabb[1], g.oy), g.rdy), tfy = __fmul_rn(__fsub_rn(aabb[4], g.oy), g.rdy);
+    if (tny > tfy) { float s = tny; tny = tfy; tfy = s; }
+    if (tn > tfy || tny > tf) { near = far = FLT_MAX; return; }
+    if (tny > tn) tn = tny;
+    if (tfy < tf) tf = tfy;
+    float tnz = __fmul_rn(__fsub_rn(aabb[2], g.oz), g.rdz), tfz = __fmul_rn(__fsub_rn(aabb[5], g.oz), g.rdz);
+    if (tnz > tfz) { float s = tnz; tnz = tfz; tfz = s; }
+    if (tn > tfz || tnz > tf) { near = far = FLT_MAX; return; }
+    if (tnz > tn) tn = tnz;
+    if (tfz < tf) tf = tfz;
+    if (tn < min_near) tn = min_near;
+    near = tn;
+    far = tf;
+}
+
+__device__ __forceinline__ float step_len(const MarchConst &mc, float t) {
+    return clampf(__fmul_rn(t, mc.dt_gamma), mc.dt_min, mc.dt_max);
+}
+
+// cell coordinate along one axis: (int)clamp(0.5 * (p * rb + 1) * H, 0, H-1) with the product taken in
+// DOUBLE because of the reference's 0.5 literal (raymarching.cu:890-892)
+__device__ __forceinline__ int cell_of(float p, float mip_rbound, const MarchConst &mc) {
+    const float u = __fadd_rn(__fmul_rn(p, mip_rbound), 1.0f);
+    const double v = __dmul_rn(__dmul_rn(0.5, (double)u), (double)mc.H);
+    return (int)clampf(__double2float_rn(v), 0.0f, mc.Hm1);
+}
+
+// Advance `t` to the next occupied sample on the ray.  On success returns true with the sample
+// position (x,y,z), its step dt, and t already advanced PAST the sample (t += dt), exactly like one
+// "occupied" iteration of the reference loop.  Returns false when t >= far (ray exhausted).
+__device__ __forceinline__ bool march_next(const MarchConst &mc, const RayGeom &g, float far, float &t, float &x,
+                                           float &y, float &z, float &dt) {
+    while (t < far) {
+        x = clampf(__fadd_rn(g.ox, __fmul_rn(t, g.dx)), -mc.bound, mc.bound);
+        y = clampf(__fadd_rn(g.oy, __fmul_rn(t, g.dy)), -mc.bound, mc.bound);
+        z = clampf(__fadd_rn(g.oz, __fmul_rn(t, g.dz)), -mc.bound, mc.bound);
+        dt = step_len(mc, t);
+        int level = 0;
+        float mip_bound = fminf(1.0f, mc.bound), mip_rbound;
+        if (mc.C > 1) {
+            int e1, e2;
+            (void)frexpf(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), &e1);
+            // mip_from_dt: dt * H in float, then * 0.5 in double, rounded to float (raymarching.cu:50)
+            (void)frexpf(__double2float_rn(__dmul_rn((double)__fmul_rn(dt, mc.fH), 0.5)), &e2);
+            const int l1 = (int)fminf(mc.fC - 1.0f, fmaxf(0.0f, (float)e1));
+            const int l2 = (int)fminf(mc.fC - 1.0f, fmaxf(0.0f, (float)e2));
+            level = max(l1, l2);
+            mip_bound = fminf(scalbnf(1.0f, level), mc.bound);
+        }
+        mip_rbound = __fdiv_rn(1.0f, mip_bound);
+        const int nx = cell_of(x, mip_rbound, mc), ny = cell_of(y, mip_rbound, mc), nz = cell_of(z, mip_rbound, mc);
+        bool occ = false;
+        const bool known_empty = (mc.bb_lo[0] <= mc.bb_hi[0]) &&
+                                 (nx < mc.bb_lo[0] || nx > mc.bb_hi[0] || ny < mc.bb_lo[1] || ny > mc.bb_hi[1] ||
+                                  nz < mc.bb_lo[2] || nz > mc.bb_hi[2]);
+        if (!known_empty) {
+            // bit index formed in float (raymarching.cu:894): exact while below 2^24
+            const uint32_t bit = (uint32_t)__fadd_rn(__fmul_rn((float)level, mc.H3),
+                                                     (float)morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
+            occ = (__ldg(mc.bits + (bit >> 3)) >> (bit & 7)) & 1;
+        }
+        if (occ) {
+            t = __fadd_rn(t, dt);
+            return true;
+        }
+        // distance to the far face of this voxel along the ray (raymarching.cu:916-919)
+        const float sx = copysignf(1.0f, g.dx), sy = copysignf(1.0f, g.dy), sz = copysignf(1.0f, g.dz);
+        const float fx = __fadd_rn(__fadd_rn((float)nx, 0.5f), __fmul_rn(0.5f, sx));
+        const float fy = __fadd_rn(__fadd_rn((float)ny, 0.5f), __fmul_rn(0.5f, sy));
+        const float fz = __fadd_rn(__fadd_rn((float)nz, 0.5f), __fmul_rn(0.5f, sz));
+        const float tx = __fmul_rn(__fsub_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(fx, mc.rH), 2.0f), 1.0f), mip_bound), x), g.rdx);
+        const float ty = __fmul_rn(__fsub_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(fy, mc.rH), 2.0f), 1.0f), mip_bound), y), g.rdy);
+        const float tz = __fmul_rn(__fsub_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(fz, mc.rH), 2.0f), 1.0f), mip_bound), z), g.rdz);
+        const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+        do {
+            t = __fadd_rn(t, step_len(mc, t));
+        } while (t < tt);
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-resolution grid (gridencoder.cu:50-84, 87-196).  Level constants are precomputed on the host
+// with the same libm calls the oracle uses (exp2f, ceil) -- see capi.cu: fill_grid_meta().
+struct GridMeta {
+    float scale[GFPP_MAX_LEVELS];      // exp2f(l*S)*H - 1
+    uint32_t offset[GFPP_MAX_LEVELS];  // table offset in entries
+    uint32_t hsize[GFPP_MAX_LEVELS];   // entries in the level
+    uint32_t mul1[GFPP_MAX_LEVELS];    // stride of dim 1 (0 if the dim is dropped: get_grid_index quirk, H5)
+    uint32_t mul2[GFPP_MAX_LEVELS];    // stride of dim 2 (0 if dropped)
+    uint32_t hashed[GFPP_MAX_LEVELS];  // 1 if gridtype==hash and the level overflows its table
+    uint32_t num_levels, dim, interp;
+    float align_off;                   // 0.5 unless align_corners
+};
+
+__device__ __forceinline__ uint32_t grid_slot(const GridMeta &gm, int l, uint32_t x, uint32_t y, uint32_t z) {
+    uint32_t idx;
+    if (gm.hashed[l]) {
+        idx = (x * 1u) ^ (y * 2654435761u) ^ (gm.dim > 2 ? z * 805459861u : 0u);
+    } else {
+        idx = x + y * gm.mul1[l] + z * gm.mul2[l];
+    }
+    const uint32_t hs = gm.hsize[l];
+    if (idx >= hs) idx %= hs;
+    return idx;
+}
+
+// 3-D, C=2 interpolation of one level for a point in [0,1]^3.  Out-of-range input => zeros.
+__device__ __forceinline__ float2 grid_lookup3(const GridMeta &gm, const float2 *__restrict__ table, int l, float u,
+                                               float v, float w) {
+    if (u < 0.f || u > 1.f || v < 0.f || v > 1.f || w < 0.f || w > 1.f) return make_float2(0.f, 0.f);
+    const float s = gm.scale[l];
+    float px = __fadd_rn(__fmul_rn(u, s), gm.align_off), py = __fadd_rn(__fmul_rn(v, s), gm.align_off),
+          pz = __fadd_rn(__fmul_rn(w, s), gm.align_off);
+    const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
+    const uint32_t gx = (uint32_t)fx0, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
+    px -= fx0; py -= fy0; pz -= fz0;
+    if (gm.interp == 1) {
+        px = px * px * (3.0f - 2.0f * px);
+        py = py * py * (3.0f - 2.0f * py);
+        pz = pz * pz * (3.0f - 2.0f * pz);
+    }
+    const float2 *tb = table + gm.offset[l];
+    float2 c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        c[i] = __ldg(tb + grid_slot(gm, l, gx + (i & 1), gy + ((i >> 1) & 1), gz + ((i >> 2) & 1)));
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        // same factor order as the reference: w = 1; w *= (x term); w *= (y term); w *= (z term)
+        float wgt = (i & 1) ? px : 1.0f - px;
+        wgt *= (i & 2) ? py : 1.0f - py;
+        wgt *= (i & 4) ? pz : 1.0f - pz;
+        acc.x += wgt * c[i].x;
+        acc.y += wgt * c[i].y;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float2 grid_lookup2(const GridMeta &gm, const float2 *__restrict__ table, int l, float u,
+                                               float v) {
+    if (u < 0.f || u > 1.f || v < 0.f || v > 1.f) return make_float2(0.f, 0.f);
+    const float s = gm.scale[l];
+    float px = __fadd_rn(__fmul_rn(u, s), gm.align_off), py = __fadd_rn(__fmul_rn(v, s), gm.align_off);
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const uint32_t gx = (uint32_t)fx0, gy = (uint32_t)fy0;
+    px -= fx0; py -= fy0;
+    if (gm.interp == 1) {
+        px = px * px * (3.0f - 2.0f * px);
+        py = py * py * (3.0f - 2.0f * py);
+    }
+    const float2 *tb = table + gm.offset[l];
+    float2 c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = __ldg(tb + grid_slot(gm, l, gx + (i & 1), gy + ((i >> 1) & 1), 0u));
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float wgt = (i & 1) ? px : 1.0f - px;
+        wgt *= (i & 2) ? py : 1.0f - py;
+        acc.x += wgt * c[i].x;
+        acc.y += wgt * c[i].y;
+    }
+    return acc;
+}
+
+// degree-4 real spherical harmonics (shencoder.cu:43-68)
+__device__ __forceinline__ void sh4(float x, float y, float z, float *o) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    o[0] = 0.28209479177387814f;
+    o[1] = -0.48860251190291987f * y;
+    o[2] = 0.48860251190291987f * z;
+    o[3] = -0.48860251190291987f * x;
+    o[4] = 1.0925484305920792f * xy;
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    o[10] = 2.8906114426405538f * xy * z;
+    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    o[14] = 1.4453057213202769f * z * (x2 - y2);
+    o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+}  // namespace gfpp

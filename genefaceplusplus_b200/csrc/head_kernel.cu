@@ -1,0 +1,588 @@
+// head_kernel.cu -- fused persistent head renderer (fp32 FFMA variant).
+//
+// Replaces the host-driven loop of NeRFRenderer.render (modules/radnerfs/renderer.py:340-384):
+//   near_far_from_aabb -> [march_rays -> GridEncoder -> ambient MLP -> GridEncoder -> sigma MLP ->
+//   SHEncoder -> color MLP -> composite_rays -> compaction]* ,  ~40 launches + 1 host sync per round,
+// with ONE persistent kernel per pass.  No intermediate (xyzs/dirs/deltas/features/activations) ever
+// leaves the SM.
+//
+// Shape of the computation
+//   * one CTA per SM, 256 threads, a pool of TM=128 ray slots; a slot is owned by thread `slot` (<128)
+//     which keeps the ray state (origin, dir, t, accumulators) in registers for the ray's lifetime;
+//   * every round each live slot contributes its next occupied sample -> a 128-row batch;
+//     dead slots are refilled from a global work cursor (persistent threads with ray refill), so batches
+//     stay full regardless of where rays terminate; rays of different frames may share a batch
+//     (the per-frame conditioning vector is part of the A tile, exactly as in the reference: K=96);
+//   * the batch runs the three MLPs as 128x128xK fp32 FFMA tile GEMMs out of shared memory; weights
+//     are streamed layer-chunk by layer-chunk through a 2-stage ring with cp.async.bulk (TMA bulk copy)
+//     + mbarrier, prefetching across layer and batch boundaries;
+//   * hash-grid features are gathered straight into the A tile (tables are L2-resident: 14.4 MB);
+//   * compositing is sequential per ray in the owner thread -> same order as the reference.
+//
+// Round-schedule exactness: the reference stops a ray after B = sum_j n_step_j samples where
+// n_step_j depends on the global alive count.  Pass 1 renders every ray up to max_steps samples and
+// histograms the death index D of each ray; k_schedule replays the n_step recurrence on the histogram
+// (it only needs counts of D < max_steps, which pass 1 knows exactly) to get B; pass 2 resumes the rays
+// that outlived max_steps for B - max_steps more samples.  No host synchronisation anywhere.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "head_kernel.cuh"
+#include "launch.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gfpp {
+
+namespace {
+
+constexpr int TM = HEAD_TM;
+constexpr int NT = HEAD_NT;
+constexpr int LDA = 148;                  // A-tile row stride in floats (16B aligned, 148 % 32 = 20)
+constexpr int LDP = 36;                   // position-feature copy stride
+constexpr int WCHUNK = 72 * 128;          // floats per weight stage (largest chunk: 72 k-rows)
+constexpr int NSTAGE = 2;
+constexpr int REFILL_ITERS = 3;
+
+struct Smem {
+    float A[TM * LDA];
+    float P[TM * LDP];
+    float W[NSTAGE * WCHUNK];
+    float narrow[8 * 128];   // rows: amb2[0..2], sigma row, col1[0..2], color-L0 bias (individual code folded)
+    float sx[TM], sy[TM], sz[TM];
+    float amb[3 * TM];
+    float sig[TM];
+    float rgb[3 * TM];
+    int frame[TM];
+    int valid[TM];
+    unsigned long long bar[NSTAGE];
+    int next, end, done;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Weight-stream state: chunk ids cycle 0..HEAD_NCHUNK-1 forever; `consumed` is uniform across the CTA.
+struct WStream {
+    uint32_t consumed;
+};
+
+__device__ __forceinline__ void issue_chunk(const HeadArgs &a, Smem &s, uint32_t seq) {
+    const uint32_t stage = seq % NSTAGE, id = seq % HEAD_NCHUNK;
+    const uint32_t bytes = (uint32_t)a.chunk_k[id] * 128u * 4u;
+    mbar_expect_tx(&s.bar[stage], bytes);
+    bulk_g2s(s.W + stage * WCHUNK, a.wide + a.chunk_off[id], bytes, &s.bar[stage]);
+}
+
+// acc[i][j] += A[row_i][kbase + k] * W[k][col_j] for k in [0, kc).   rows: ty*4+i (i<4), 64+ty*4+(i-4);
+// cols: tx*4+j (j<4), 64+tx*4+(j-4).  A is row-major (stride LDA), W is k-major [kc][128].
+__device__ __forceinline__ void ffma_chunk(float (&acc)[8][8], const float *__restrict__ sA, const float *__restrict__ sW,
+                                           int kbase, int kc, int ty, int tx) {
+    const float *a0 = sA + (ty * 4) * LDA + kbase;
+    const float *a1 = sA + (64 + ty * 4) * LDA + kbase;
+    const float *w = sW + tx * 4;
+#pragma unroll 2
+    for (int k4 = 0; k4 < kc; k4 += 4) {
+        float4 av[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            av[i] = *reinterpret_cast<const float4 *>(a0 + i * LDA + k4);
+            av[4 + i] = *reinterpret_cast<const float4 *>(a1 + i * LDA + k4);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const float4 b0 = *reinterpret_cast<const float4 *>(w + (k4 + kk) * 128);
+            const float4 b1 = *reinterpret_cast<const float4 *>(w + (k4 + kk) * 128 + 64);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float ai = kk == 0 ? av[i].x : kk == 1 ? av[i].y : kk == 2 ? av[i].z : av[i].w;
+                acc[i][0] = fmaf(ai, b0.x, acc[i][0]);
+                acc[i][1] = fmaf(ai, b0.y, acc[i][1]);
+                acc[i][2] = fmaf(ai, b0.z, acc[i][2]);
+                acc[i][3] = fmaf(ai, b0.w, acc[i][3]);
+                acc[i][4] = fmaf(ai, b1.x, acc[i][4]);
+                acc[i][5] = fmaf(ai, b1.y, acc[i][5]);
+                acc[i][6] = fmaf(ai, b1.z, acc[i][6]);
+                acc[i][7] = fmaf(ai, b1.w, acc[i][7]);
+            }
+        }
+    }
+}
+
+// One 128x128xK layer: consume `nchunks` chunks from the stream, then write act(acc + bias) to A[:, coff:coff+128].
+template <bool RELU>
+__device__ __forceinline__ void wide_layer(const HeadArgs &a, Smem &s, WStream &ws, int nchunks, int coff,
+                                           const float *bias, int tid) {
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    int kbase = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const uint32_t seq = ws.consumed, stage = seq % NSTAGE, id = seq % HEAD_NCHUNK;
+        const int kc = a.chunk_k[id];
+        mbar_wait(&s.bar[stage], (seq / NSTAGE) & 1);
+        ffma_chunk(acc, s.A, s.W + stage * WCHUNK, kbase, kc, ty, tx);
+        kbase += kc;
+        ws.consumed = seq + 1;
+        __syncthreads();  // everyone is done with this stage (and, after the last chunk, with reading A)
+        if (tid == 0) issue_chunk(a, s, seq + NSTAGE);
+    }
+    float bv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bv[j] = bias ? bias[(j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4))] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = acc[i][j] + bv[j];
+            if (RELU) v[j] = fmaxf(v[j], 0.f);
+        }
+        float *dst = s.A + row * LDA + coff + tx * 4;
+        *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(dst + 64) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+}
+
+// dot products of every row of A[:, 0:128] with NOUT narrow weight rows; both lanes of a pair get the sums.
+template <int NOUT>
+__device__ __forceinline__ void narrow_dot(const Smem &s, const float *wrow, int tid, float (&out)[NOUT]) {
+    const int row = tid >> 1, half = tid & 1;
+    const float *ar = s.A + row * LDA + half * 64;
+    float v[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) v[o] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 64; k += 4) {
+        const float4 x = *reinterpret_cast<const float4 *>(ar + k);
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+            const float4 w = *reinterpret_cast<const float4 *>(wrow + o * 128 + half * 64 + k);
+            v[o] = fmaf(x.x, w.x, v[o]);
+            v[o] = fmaf(x.y, w.y, v[o]);
+            v[o] = fmaf(x.z, w.z, v[o]);
+            v[o] = fmaf(x.w, w.w, v[o]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) out[o] = v[o] + __shfl_xor_sync(0xffffffffu, v[o], 1);
+}
+
+// add `val` to base[key] once per distinct key in the warp's active lanes
+__device__ __forceinline__ void warp_agg_add(int *base, int key, int val) {
+    const unsigned act = __activemask();
+    const unsigned grp = __match_any_sync(act, key);
+    const int sum = __reduce_add_sync(grp, val);
+    if ((int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(base + key, sum);
+}
+
+struct Slot {
+    RayGeom g;
+    float t, near, far, ws, depth, r, gch, b;
+    float px, py, pz, dt;  // pending sample
+    int gid, frame, nsamp, cap;
+    bool active;
+};
+
+__device__ __forceinline__ void load_ray(const HeadArgs &a, int frame, int ray, RayGeom &g) {
+    if (a.rays_o) {
+        const size_t o = ((size_t)frame * a.n_rays + ray) * 3;
+        ray_geom_init(g, a.rays_o[o], a.rays_o[o + 1], a.rays_o[o + 2], a.rays_d[o], a.rays_d[o + 1], a.rays_d[o + 2]);
+    } else {
+        // get_rays (modules/radnerfs/utils.py:302-360): pixel centre, normalise, rotate by c2w[:3,:3]
+        const float *P = a.poses + (size_t)frame * 16;
+        const int row = ray / a.img_w, col = ray - row * a.img_w;
+        const float xs = __fdiv_rn(__fsub_rn((float)col + 0.5f, a.cx), a.fx);
+        const float ys = __fdiv_rn(__fsub_rn((float)row + 0.5f, a.cy), a.fy);
+        const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(xs, xs), __fmul_rn(ys, ys)), 1.0f));
+        const float dxc = __fdiv_rn(xs, nrm), dyc = __fdiv_rn(ys, nrm), dzc = __fdiv_rn(1.0f, nrm);
+        float d[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            d[k] = __fadd_rn(__fadd_rn(__fmul_rn(dxc, P[4 * k]), __fmul_rn(dyc, P[4 * k + 1])), __fmul_rn(dzc, P[4 * k + 2]));
+        ray_geom_init(g, P[3], P[7], P[11], d[0], d[1], d[2]);
+    }
+}
+
+// conservative: can the segment [near, far] of the ray touch the (one-cell padded) box of occupied voxels?
+__device__ __forceinline__ bool may_hit_occupied(bool have_box, const float (&occ_lo)[3], const float (&occ_hi)[3],
+                                                 const RayGeom &g, float near, float far) {
+    if (!have_box) return true;
+    float t0 = near, t1 = far;
+    const float o[3] = {g.ox, g.oy, g.oz}, rd[3] = {g.rdx, g.rdy, g.rdz}, d[3] = {g.dx, g.dy, g.dz};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (d[k] == 0.f) {
+            if (o[k] < occ_lo[k] || o[k] > occ_hi[k]) return false;
+            continue;
+        }
+        float ta = (occ_lo[k] - o[k]) * rd[k], tb = (occ_hi[k] - o[k]) * rd[k];
+        if (ta > tb) { const float s = ta; ta = tb; tb = s; }
+        t0 = fmaxf(t0, ta);
+        t1 = fminf(t1, tb);
+    }
+    return t0 <= t1;
+}
+
+__device__ __forceinline__ void finalize_ray(const HeadArgs &a, const Slot &s, bool normalise_depth) {
+    const size_t g = (size_t)s.gid;
+    a.image[3 * g] = s.r;
+    a.image[3 * g + 1] = s.gch;
+    a.image[3 * g + 2] = s.b;
+    a.wsum[g] = s.ws;
+    // renderer.py:394: depth = clamp(depth - nears, min=0) / (fars - nears)
+    a.depth[g] = normalise_depth ? __fdiv_rn(fmaxf(__fsub_rn(s.depth, s.near), 0.f), __fsub_rn(s.far, s.near)) : s.depth;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ HeadArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x;
+
+    // ---- one-time setup ----
+    MarchConst mc = a.mc;
+    // padded world-space box of the occupied voxels: rays whose [near, far] segment misses it have no sample.
+    // Only valid for a single cascade whose aabb lies inside the cube (host sets use_occ_box accordingly).
+    float occ_lo[3] = {0.f, 0.f, 0.f}, occ_hi[3] = {0.f, 0.f, 0.f};
+    bool have_box = false;
+    if (a.occ_bounds) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { mc.bb_lo[k] = a.occ_bounds[k]; mc.bb_hi[k] = a.occ_bounds[3 + k]; }
+        if (a.use_occ_box) {
+            have_box = true;
+            const float mb = fminf(1.0f, mc.bound);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (mc.bb_hi[k] < mc.bb_lo[k]) { occ_lo[k] = 1e30f; occ_hi[k] = -1e30f; }  // nothing occupied
+                else {
+                    occ_lo[k] = ((float)(mc.bb_lo[k] - 1) * mc.rH * 2.0f - 1.0f) * mb;
+                    occ_hi[k] = ((float)(mc.bb_hi[k] + 2) * mc.rH * 2.0f - 1.0f) * mb;
+                }
+            }
+        }
+    }
+    for (int i = tid; i < 8 * 128; i += NT) s.narrow[i] = a.narrow[i];
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; ++i) mbar_init(&s.bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s.next = 0; s.end = 0; s.done = 0;
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (uint32_t q = 0; q < NSTAGE; ++q) issue_chunk(a, s, q);
+    WStream wst;
+    wst.consumed = 0;
+
+    const int total = (a.pass == 1) ? a.n_frames * a.n_rays : *a.n_survivors;
+    Slot sl;
+    sl.active = false;
+    sl.gid = 0; sl.frame = 0; sl.nsamp = 0; sl.cap = 0;
+
+    for (;;) {
+        // ================= refill dead slots from the global cursor =================
+        for (int it = 0; it < REFILL_ITERS; ++it) {
+            if (tid == 0 && s.next >= s.end && !s.done) {
+                const int base = atomicAdd(a.cursor, TM);
+                if (base >= total) { s.done = 1; }
+                else { s.next = base; s.end = min(base + TM, total); }
+            }
+            __syncthreads();
+            if (tid < TM && !sl.active && s.next < s.end) {
+                const int w = atomicAdd(&s.next, 1);
+                if (w < s.end) {
+                    int gid = w;
+                    if (a.pass == 2) gid = a.survivors[w];
+                    sl.gid = gid;
+                    sl.frame = gid / a.n_rays;
+                    const int ray = gid - sl.frame * a.n_rays;
+                    load_ray(a, sl.frame, ray, sl.g);
+                    near_far(sl.g, a.aabb, a.min_near, sl.near, sl.far);
+                    bool live;
+                    if (a.pass == 1) {
+                        sl.t = sl.near; sl.ws = 0.f; sl.depth = 0.f; sl.r = sl.gch = sl.b = 0.f;
+                        sl.nsamp = 0; sl.cap = a.max_steps;
+                        live = may_hit_occupied(have_box, occ_lo, occ_hi, sl.g, sl.near, sl.far) &&
+                               march_next(mc, sl.g, sl.far, sl.t, sl.px, sl.py, sl.pz, sl.dt);
+                        if (!live) {  // no sample at all: the ray dies at position 1 (delta == 0)
+                            finalize_ray(a, sl, true);
+                            warp_agg_add(a.hist, sl.frame * (a.max_steps + 2) + 1, 1);
+                        }
+                    } else {
+                        const size_t g = (size_t)gid;
+                        sl.t = a.rays_t[g]; sl.ws = a.wsum[g]; sl.depth = a.depth[g];
+                        sl.r = a.image[3 * g]; sl.gch = a.image[3 * g + 1]; sl.b = a.image[3 * g + 2];
+                        sl.nsamp = a.max_steps; sl.cap = a.B_total[sl.frame];
+                        live = sl.nsamp < sl.cap && march_next(mc, sl.g, sl.far, sl.t, sl.px, sl.py, sl.pz, sl.dt);
+                        if (!live) finalize_ray(a, sl, true);
+                    }
+                    sl.active = live;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ================= publish the batch =================
+        if (tid < TM) {
+            s.valid[tid] = sl.active ? 1 : 0;
+            s.frame[tid] = sl.frame;
+            s.sx[tid] = sl.px; s.sy[tid] = sl.py; s.sz[tid] = sl.pz;
+        }
+        const int n_valid = __syncthreads_count(tid < TM && sl.active);
+        if (n_valid == 0) {
+            const bool out_of_work = s.done && s.next >= s.end;
+            __syncthreads();  // thread 0 must not start the next refill (which rewrites next/end/done) before everyone has read them
+            if (out_of_work) break;
+            continue;
+        }
+
+        const int slot = tid & (TM - 1), lg = tid >> 7;
+        const bool v = s.valid[slot] != 0;
+        // ---- position grid -> A[:, 0:32] (+ copy in P); conditioning -> A[:, 32:96] ----
+        {
+            float *ar = s.A + slot * LDA, *pr = s.P + slot * LDP;
+            if (v) {
+                const float inv2b = 2.0f * mc.bound;
+                const float u = __fdiv_rn(__fadd_rn(s.sx[slot], mc.bound), inv2b);
+                const float vv = __fdiv_rn(__fadd_rn(s.sy[slot], mc.bound), inv2b);
+                const float w = __fdiv_rn(__fadd_rn(s.sz[slot], mc.bound), inv2b);
+#pragma unroll 2
+                for (int l = lg * 8; l < lg * 8 + 8; ++l) {
+                    const float2 f = grid_lookup3(a.pos_gm, a.pos_tab, l, u, vv, w);
+                    *reinterpret_cast<float2 *>(ar + 2 * l) = f;
+                    *reinterpret_cast<float2 *>(pr + 2 * l) = f;
+                }
+                const float4 *cf = reinterpret_cast<const float4 *>(a.cond_feat + (size_t)s.frame[slot] * 64 + lg * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<float4 *>(ar + 32 + lg * 32 + 4 * j) = __ldg(cf + j);
+            } else {
+                for (int l = lg * 8; l < lg * 8 + 8; ++l) {
+                    *reinterpret_cast<float2 *>(ar + 2 * l) = make_float2(0.f, 0.f);
+                    *reinterpret_cast<float2 *>(pr + 2 * l) = make_float2(0.f, 0.f);
+                }
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4 *>(ar + 32 + lg * 32 + 4 * j) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncthreads();
+
+        // ---- ambient net 96 -> 128 -> 128 -> 3, tanh (radnerf.py:120-122) ----
+        wide_layer<true>(a, s, wst, 2, 0, nullptr, tid);
+        wide_layer<true>(a, s, wst, 2, 0, nullptr, tid);
+        {
+            float o[3];
+            narrow_dot<3>(s, s.narrow, tid, o);
+            if ((tid & 1) == 0) {
+                const int row = tid >> 1;
+                s.amb[row] = tanhf(o[0]);
+                s.amb[TM + row] = tanhf(o[1]);
+                s.amb[2 * TM + row] = tanhf(o[2]);
+            }
+        }
+        __syncthreads();
+        // ---- ambient grid -> A[:, 32:64]; A[:, 0:32] <- position features (radnerf.py:123-126) ----
+        {
+            float *ar = s.A + slot * LDA;
+            const float *pr = s.P + slot * LDP;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4 *>(ar + lg * 16 + 4 * j) = *reinterpret_cast<const float4 *>(pr + lg * 16 + 4 * j);
+            if (v) {
+                // GridEncoder.forward with bound=1: (x + 1) / 2
+                const float u = __fdiv_rn(__fadd_rn(s.amb[slot], 1.0f), 2.0f);
+                const float vv = __fdiv_rn(__fadd_rn(s.amb[TM + slot], 1.0f), 2.0f);
+                const float w = __fdiv_rn(__fadd_rn(s.amb[2 * TM + slot], 1.0f), 2.0f);
+#pragma unroll 2
+                for (int l = lg * 8; l < lg * 8 + 8; ++l) {
+                    const float2 f = (a.amb_gm.dim == 3) ? grid_lookup3(a.amb_gm, a.amb_tab, l, u, vv, w)
+                                                         : grid_lookup2(a.amb_gm, a.amb_tab, l, u, vv);
+                    *reinterpret_cast<float2 *>(ar + 32 + 2 * l) = f;
+                }
+            } else {
+                for (int l = lg * 8; l < lg * 8 + 8; ++l) *reinterpret_cast<float2 *>(ar + 32 + 2 * l) = make_float2(0.f, 0.f);
+            }
+        }
+        __syncthreads();
+
+        // ---- sigma net 64 -> 128 -> 128 -> (1 + 128) (radnerf.py:126-130) ----
+        wide_layer<true>(a, s, wst, 1, 0, nullptr, tid);
+        wide_layer<true>(a, s, wst, 2, 0, nullptr, tid);
+        {
+            float o[1];
+            narrow_dot<1>(s, s.narrow + 3 * 128, tid, o);
+            // trunc_exp forward is plain exp (utils.py:36-41); sigmas *= density_scale (renderer.py:376)
+            if ((tid & 1) == 0) s.sig[tid >> 1] = a.density_scale * expf(o[0]);
+        }
+        // geo features (no activation) -> A[:, 16:144]; the k-loop only reads A, the write happens after its
+        // trailing barrier, so the sigma dot above needs no extra sync.
+        {
+            const int ty = tid >> 4, tx = tid & 15;
+            float acc[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+            int kbase = 0;
+            for (int c = 0; c < 2; ++c) {
+                const uint32_t seq = wst.consumed, stage = seq % NSTAGE, id = seq % HEAD_NCHUNK;
+                const int kc = a.chunk_k[id];
+                mbar_wait(&s.bar[stage], (seq / NSTAGE) & 1);
+                ffma_chunk(acc, s.A, s.W + stage * WCHUNK, kbase, kc, ty, tx);
+                kbase += kc;
+                wst.consumed = seq + 1;
+                __syncthreads();
+                if (tid == 0) issue_chunk(a, s, seq + NSTAGE);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+                float *dst = s.A + row * LDA + 16 + tx * 4;
+                *reinterpret_cast<float4 *>(dst) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                *reinterpret_cast<float4 *>(dst + 64) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+            }
+            if (tid < TM) {  // SH(dir) -> A[:, 0:16] (radnerf.py:132-134)
+                float sh[16];
+                sh4(sl.g.dx, sl.g.dy, sl.g.dz, sh);
+                float *dst = s.A + tid * LDA;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4 *>(dst + 4 * j) = sl.active ? make_float4(sh[4 * j], sh[4 * j + 1], sh[4 * j + 2], sh[4 * j + 3])
+                                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncthreads();
+        }
+
+        // ---- color net (16 + 128 [+ 4 folded into the bias]) -> 128 -> 3, sigmoid (radnerf.py:134-139) ----
+        wide_layer<true>(a, s, wst, 2, 0, s.narrow + 7 * 128, tid);
+        {
+            float o[3];
+            narrow_dot<3>(s, s.narrow + 4 * 128, tid, o);
+            if ((tid & 1) == 0) {
+                const int row = tid >> 1;
+                s.rgb[row] = 1.0f / (1.0f + expf(-o[0]));
+                s.rgb[TM + row] = 1.0f / (1.0f + expf(-o[1]));
+                s.rgb[2 * TM + row] = 1.0f / (1.0f + expf(-o[2]));
+            }
+        }
+        __syncthreads();
+
+        // ================= composite (raymarching.cu:978-1006) + advance =================
+        if (tid < TM && sl.active) {
+            const float sigma = s.sig[tid];
+            const float alpha = 1.0f - expf(-sigma * sl.dt);
+            const float T = 1.0f - sl.ws;
+            const float w = alpha * T;
+            sl.ws += w;
+            sl.depth += w * sl.t;  // sl.t is already the post-sample t (deltas[1])
+            sl.r += w * s.rgb[tid];
+            sl.gch += w * s.rgb[TM + tid];
+            sl.b += w * s.rgb[2 * TM + tid];
+            sl.nsamp += 1;
+            if (a.valid_samples) warp_agg_add(a.valid_samples, sl.frame, 1);
+            int D = 0;  // death index (1-based sample position), 0 = still alive
+            bool suspend = false;
+            if (T < a.T_thresh) D = sl.nsamp;
+            else if (sl.nsamp >= sl.cap) suspend = true;
+            else if (!march_next(mc, sl.g, sl.far, sl.t, sl.px, sl.py, sl.pz, sl.dt)) D = sl.nsamp + 1;
+            if (D) {
+                finalize_ray(a, sl, true);
+                if (a.pass == 1) warp_agg_add(a.hist, sl.frame * (a.max_steps + 2) + D, 1);
+                sl.active = false;
+            } else if (suspend) {
+                if (a.pass == 1) {
+                    finalize_ray(a, sl, false);  // raw depth: pass 2 keeps accumulating
+                    a.rays_t[sl.gid] = sl.t;
+                    cg::coalesced_group grp = cg::coalesced_threads();
+                    int base = 0;
+                    if (grp.thread_rank() == 0) base = atomicAdd(a.n_survivors, (int)grp.size());
+                    base = grp.shfl(base, 0);
+                    a.survivors[base + grp.thread_rank()] = sl.gid;
+                } else {
+                    finalize_ray(a, sl, true);
+                }
+                sl.active = false;
+            }
+        }
+        // no barrier needed here: the refill loop starts with one before smem is touched again
+    }
+
+    // drain the prefetched weight chunks before the CTA (and its shared memory) goes away
+    for (uint32_t q = 0; q < NSTAGE; ++q) {
+        const uint32_t seq = wst.consumed + q;
+        mbar_wait(&s.bar[seq % NSTAGE], (seq / NSTAGE) & 1);
+    }
+}
+
+// Replays the reference's round schedule (renderer.py:354-384) on the death histogram of each frame:
+//   n_step_j = clamp(N // n_alive_j, 1, 8);  cum += n_step_j;  n_alive_{j+1} = #{D > cum};  until cum >= max_steps.
+__global__ void k_schedule(const int *__restrict__ hist, int n_frames, int n_rays, int max_steps, int *__restrict__ B_total) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    const int *h = hist + (size_t)f * (max_steps + 2);
+    int cum = 0, alive = n_rays, dead_upto = 0, scanned = 0;
+    while (cum < max_steps && alive > 0) {
+        int n_step = n_rays / alive;
+        n_step = n_step < 1 ? 1 : (n_step > 8 ? 8 : n_step);
+        cum += n_step;
+        const int lim = cum < max_steps + 1 ? cum : max_steps + 1;
+        while (scanned < lim) { ++scanned; dead_upto += h[scanned]; }
+        alive = n_rays - dead_upto;
+    }
+    B_total[f] = cum;
+}
+
+size_t head_smem_bytes() { return sizeof(Smem); }
+
+cudaError_t launch_head(const HeadArgs &a, int total_hint, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int blocks = sm_count();
+    if (total_hint >= 0) {
+        const int need = (total_hint + TM - 1) / TM;
+        if (need < blocks) blocks = need > 0 ? need : 1;
+    }
+    k_head<<<blocks, NT, sizeof(Smem), st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_schedule(const int *hist, int n_frames, int n_rays, int max_steps, int *B_total, cudaStream_t st) {
+    k_schedule<<<(n_frames + 63) / 64, 64, 0, st>>>(hist, n_frames, n_rays, max_steps, B_total);
+    return cudaGetLastError();
+}
+
+}  // namespace gfpp

@@ -1,0 +1,51 @@
+// head_kernel.cuh -- argument block of the fused head renderer (see head_kernel.cu).
+#pragma once
+#include "common.cuh"
+
+namespace gfpp {
+
+constexpr int HEAD_TM = 128;      // samples per batch == ray slots per CTA
+constexpr int HEAD_NT = 256;      // threads per CTA
+constexpr int HEAD_NCHUNK = 11;   // weight chunks streamed per batch (see pack_head_weights in capi.cu)
+
+struct HeadArgs {
+    // ---- model ----
+    GridMeta pos_gm, amb_gm;
+    const float2 *pos_tab, *amb_tab;
+    const float *wide;              // concatenated k-major weight chunks, stream order
+    int chunk_off[HEAD_NCHUNK];     // float offset of each chunk in `wide`
+    int chunk_k[HEAD_NCHUNK];       // k-rows in each chunk (<= 72, multiple of 4)
+    const float *narrow;            // [8][128]: ambient out rows 0-2, sigma row, color out rows 0-2, color-L0 bias
+    MarchConst mc;
+    const int *occ_bounds;          // device [6] tight occupied-cell bounds (or nullptr)
+    float aabb[6];
+    float min_near, density_scale;
+    int use_occ_box;                // 1: reject rays that miss the padded box of occupied voxels (cascade==1, aabb inside cube)
+    // ---- frames ----
+    int n_frames, n_rays;
+    const float *rays_o, *rays_d;   // [F,N,3] or nullptr (then rays come from poses + intrinsics)
+    const float *poses;             // [F,16]
+    float fx, fy, cx, cy;
+    int img_w;
+    const float *cond_feat;         // [F,64]
+    int max_steps;
+    float T_thresh;
+    // ---- outputs / state ----
+    float *image;                   // [F,N,3] premultiplied head colour (before background)
+    float *wsum;                    // [F,N]
+    float *depth;                   // [F,N]
+    float *rays_t;                  // [F,N] resume point of rays that outlive max_steps
+    int *hist;                      // [F, max_steps+2] death-index histogram
+    int *survivors;                 // [F*N] global ray ids still alive after max_steps samples
+    int *n_survivors;               // [1]
+    int *cursor;                    // [1] global work cursor
+    int *B_total;                   // [F] per-frame sample cap produced by k_schedule
+    int *valid_samples;             // [F] statistics (or nullptr)
+    int pass;                       // 1 or 2
+};
+
+size_t head_smem_bytes();
+cudaError_t launch_head(const HeadArgs &a, int total_hint, cudaStream_t st);
+cudaError_t launch_schedule(const int *hist, int n_frames, int n_rays, int max_steps, int *B_total, cudaStream_t st);
+
+}  // namespace gfpp

@@ -1,0 +1,226 @@
+// ops_kernels.cu -- per-op kernels behind the (A) level of include/gfpp.h.
+//
+// These mirror the six inference ops of the reference's extensions one-to-one so that (i) the reference's
+// unmodified Python wrappers can run on this library and (ii) each op can be parity-tested in isolation
+// against the C oracle and against the reference's own kernels (oracle/_ref).  The production path is the
+// fused renderer in head_kernel.cu / torso_kernel.cu; these kernels are simple grid-stride SIMT kernels
+// sized in multiples of the SM count.
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace gfpp {
+
+// ---- near_far_from_aabb (raymarching.cu:91-145) ----
+__global__ void k_near_far(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                           const float *__restrict__ aabb, uint32_t N, float min_near, float *__restrict__ nears,
+                           float *__restrict__ fars) {
+    float bb[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) bb[i] = __ldg(aabb + i);
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        RayGeom g;
+        ray_geom_init(g, rays_o[3 * n], rays_o[3 * n + 1], rays_o[3 * n + 2], rays_d[3 * n], rays_d[3 * n + 1],
+                      rays_d[3 * n + 2]);
+        float nr, fr;
+        near_far(g, bb, min_near, nr, fr);
+        nears[n] = nr;
+        fars[n] = fr;
+    }
+}
+
+// ---- march_rays (raymarching.cu:827-929): one round, up to n_step samples per alive ray ----
+__global__ void k_march_rays(MarchConst mc, uint32_t n_alive, uint32_t n_step, const int32_t *__restrict__ rays_alive,
+                             const float *__restrict__ rays_t, const float *__restrict__ rays_o,
+                             const float *__restrict__ rays_d, const float *__restrict__ fars, float *__restrict__ xyzs,
+                             float *__restrict__ dirs, float *__restrict__ deltas, const float *__restrict__ noises) {
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < n_alive; n += gridDim.x * blockDim.x) {
+        const int ray = rays_alive[n];
+        RayGeom g;
+        ray_geom_init(g, rays_o[3 * ray], rays_o[3 * ray + 1], rays_o[3 * ray + 2], rays_d[3 * ray],
+                      rays_d[3 * ray + 1], rays_d[3 * ray + 2]);
+        float t = rays_t[ray];
+        const float far = fars[ray];
+        // optional jitter (zero on the inference path): t += clamp(t*dt_gamma) * noise
+        t = __fadd_rn(t, __fmul_rn(step_len(mc, t), noises[n]));
+        float *px = xyzs + (size_t)n * n_step * 3, *pd = dirs + (size_t)n * n_step * 3,
+              *pl = deltas + (size_t)n * n_step * 2;
+        for (uint32_t s = 0; s < n_step; ++s) {
+            float x, y, z, dt;
+            if (!march_next(mc, g, far, t, x, y, z, dt)) break;
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = g.dx; pd[1] = g.dy; pd[2] = g.dz;
+            pl[0] = dt; pl[1] = t;
+            px += 3; pd += 3; pl += 2;
+        }
+    }
+}
+
+// ---- composite_rays (raymarching.cu:942-1029) ----
+__global__ void k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *__restrict__ rays_alive,
+                                 float *__restrict__ rays_t, const float *__restrict__ sigmas,
+                                 const float *__restrict__ rgbs, const float *__restrict__ deltas,
+                                 float *__restrict__ weights_sum, float *__restrict__ depth, float *__restrict__ image) {
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < n_alive; n += gridDim.x * blockDim.x) {
+        const int ray = rays_alive[n];
+        const float *sg = sigmas + (size_t)n * n_step, *cl = rgbs + (size_t)n * n_step * 3,
+                    *dl = deltas + (size_t)n * n_step * 2;
+        float t = rays_t[ray], ws = weights_sum[ray], dp = depth[ray];
+        float r = image[3 * ray], g = image[3 * ray + 1], b = image[3 * ray + 2];
+        uint32_t step = 0;
+        while (step < n_step) {
+            if (dl[0] == 0) break;
+            const float alpha = 1.0f - expf(-sg[0] * dl[0]);  // accurate expf, not __expf
+            const float T = 1.0f - ws;
+            const float w = alpha * T;
+            ws += w;
+            t = dl[1];
+            dp += w * t;
+            r += w * cl[0];
+            g += w * cl[1];
+            b += w * cl[2];
+            if (T < T_thresh) break;
+            ++sg; cl += 3; dl += 2; ++step;
+        }
+        if (step < n_step) rays_alive[n] = -1;
+        else rays_t[ray] = t;
+        weights_sum[ray] = ws;
+        depth[ray] = dp;
+        image[3 * ray] = r; image[3 * ray + 1] = g; image[3 * ray + 2] = b;
+    }
+}
+
+// ---- grid_encode_forward (gridencoder.cu:87-196), outputs [L,B,2] ----
+template <int D>
+__global__ void k_grid_encode(GridMeta gm, const float *__restrict__ inputs, const float2 *__restrict__ table,
+                              float2 *__restrict__ outputs, uint32_t B) {
+    const uint32_t total = B * gm.num_levels;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t l = i / B, b = i - l * B;  // level-major: a warp works on one level of neighbouring points
+        float2 f;
+        if (D == 3) f = grid_lookup3(gm, table, l, inputs[3 * b], inputs[3 * b + 1], inputs[3 * b + 2]);
+        else f = grid_lookup2(gm, table, l, inputs[2 * b], inputs[2 * b + 1]);
+        outputs[(size_t)l * B + b] = f;
+    }
+}
+
+// ---- sh_encode_forward (shencoder.cu:27-68), degree <= 4 ----
+__global__ void k_sh_encode(const float *__restrict__ inputs, float *__restrict__ outputs, uint32_t B, uint32_t degree) {
+    const uint32_t C2 = degree * degree;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        float o[16];
+        sh4(inputs[3 * b], inputs[3 * b + 1], inputs[3 * b + 2], o);
+        for (uint32_t c = 0; c < C2; ++c) outputs[(size_t)b * C2 + c] = o[c];
+    }
+}
+
+// ---- freq_encode_forward (freqencoder.cu:30-58); accurate sinf instead of __sinf ----
+__global__ void k_freq_encode(const float *__restrict__ inputs, uint32_t B, uint32_t D, uint32_t C,
+                              float *__restrict__ outputs) {
+    const uint32_t total = B * C;
+    const float half_pi = 3.141592653589793f / 2;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t b = i / C, c = i - b * C;
+        float v;
+        if (c < D) {
+            v = inputs[b * D + c];
+        } else {
+            const uint32_t col = c / D - 1, d = c % D, f = col / 2;
+            v = sinf(__fadd_rn(scalbnf(inputs[b * D + d], (int)f), (float)(col % 2) * half_pi));
+        }
+        outputs[i] = v;
+    }
+}
+
+// ---- tight cell bounds of the occupied voxels (used to skip bit reads in known-empty space) ----
+// bounds[0..2] = min cell, bounds[3..5] = max cell over all cascades; initialised by the caller to
+// {INT_MAX.., -1..}.  Cells are decoded from the Morton bit index.
+__device__ __forceinline__ uint32_t compact3(uint32_t x) {
+    x &= 0x49249249u;
+    x = (x | (x >> 2)) & 0xC30C30C3u;
+    x = (x | (x >> 4)) & 0x0F00F00Fu;
+    x = (x | (x >> 8)) & 0xFF0000FFu;
+    x = (x | (x >> 16)) & 0x0000FFFFu;
+    return x;
+}
+
+__global__ void k_occupancy_bounds(const uint8_t *__restrict__ bits, uint32_t n_bytes, uint32_t H3, int *bounds) {
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {-1, -1, -1};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_bytes; i += gridDim.x * blockDim.x) {
+        uint32_t v = bits[i];
+        while (v) {
+            const int k = __ffs(v) - 1;
+            v &= v - 1;
+            const uint32_t m = (i * 8u + k) % H3;
+            const int c[3] = {(int)compact3(m), (int)compact3(m >> 1), (int)compact3(m >> 2)};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], c[a]); hi[a] = max(hi[a], c[a]); }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (lo[a] != INT_MAX) atomicMin(bounds + a, lo[a]);
+            if (hi[a] >= 0) atomicMax(bounds + 3 + a, hi[a]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+cudaError_t launch_near_far(const float *rays_o, const float *rays_d, const float *aabb, uint32_t N, float min_near,
+                            float *nears, float *fars, cudaStream_t st) {
+    if (N == 0) return cudaSuccess;
+    k_near_far<<<grid_for(N, 256), 256, 0, st>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_march_rays(const MarchConst &mc, uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive,
+                              const float *rays_t, const float *rays_o, const float *rays_d, const float *fars,
+                              float *xyzs, float *dirs, float *deltas, const float *noises, cudaStream_t st) {
+    if (n_alive == 0) return cudaSuccess;
+    k_march_rays<<<grid_for(n_alive, 128), 128, 0, st>>>(mc, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, fars,
+                                                          xyzs, dirs, deltas, noises);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive, float *rays_t,
+                                  const float *sigmas, const float *rgbs, const float *deltas, float *weights_sum,
+                                  float *depth, float *image, cudaStream_t st) {
+    if (n_alive == 0) return cudaSuccess;
+    k_composite_rays<<<grid_for(n_alive, 128), 128, 0, st>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs,
+                                                              deltas, weights_sum, depth, image);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grid_encode(const GridMeta &gm, const float *inputs, const float *table, float *outputs, uint32_t B,
+                               cudaStream_t st) {
+    if (B == 0) return cudaSuccess;
+    const uint32_t total = B * gm.num_levels;
+    if (gm.dim == 3)
+        k_grid_encode<3><<<grid_for(total, 256), 256, 0, st>>>(gm, inputs, (const float2 *)table, (float2 *)outputs, B);
+    else
+        k_grid_encode<2><<<grid_for(total, 256), 256, 0, st>>>(gm, inputs, (const float2 *)table, (float2 *)outputs, B);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sh_encode(const float *inputs, float *outputs, uint32_t B, uint32_t degree, cudaStream_t st) {
+    if (B == 0) return cudaSuccess;
+    k_sh_encode<<<grid_for(B, 256), 256, 0, st>>>(inputs, outputs, B, degree);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_freq_encode(const float *inputs, uint32_t B, uint32_t D, uint32_t C, float *outputs, cudaStream_t st) {
+    if (B * C == 0) return cudaSuccess;
+    k_freq_encode<<<grid_for(B * C, 256), 256, 0, st>>>(inputs, B, D, C, outputs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_occupancy_bounds(const uint8_t *bits, uint32_t n_bytes, uint32_t H3, int *bounds, cudaStream_t st) {
+    k_occupancy_bounds<<<grid_for(n_bytes, 256), 256, 0, st>>>(bits, n_bytes, H3, bounds);
+    return cudaGetLastError();
+}
+
+}  // namespace gfpp

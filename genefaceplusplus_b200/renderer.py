@@ -1,0 +1,447 @@
+"""B200 drop-ins for the reference's model API ("B-model").
+
+`RADNeRF` / `RADNeRFTorso` here mirror modules/radnerfs/radnerf.py:13 and modules/radnerfs/radnerf_torso.py:17:
+  * same constructor argument (the hparams dict), same parameter / buffer names and shapes, so
+    `load_ckpt(model, dir, strict=True)` (utils/commons/ckpt_utils.py:29-76) and `.to(device).eval()` work;
+  * same `render(rays_o, rays_d, cond, bg_coords, poses, index, dt_gamma, bg_color, perturb, force_all_rays,
+    max_steps, T_thresh, ..., **kwargs)` signature and result dict (renderer.py:286 / radnerf_torso.py:86),
+    tolerant of every extra kwarg the driver passes (`staged`, `lm68`, all hparams keys);
+  * same errors-as-exceptions behaviour.
+Everything under `render` runs in the fused sm_100a kernels of libgfpp.so through the C-ABI (include/gfpp.h).
+Only the tiny conditioning nets (AudioNet / AudioAttNet, cond_encoder.py:98-180: 5x204 -> 64) stay in PyTorch,
+as SURVEY.md 8(a) a4 prescribes.  Inference only: `self.training` raises (training is out of scope).
+
+`render_clip` is the B200-first entry point: a whole clip of poses + conditioning is
+rendered by a handful of persistent-kernel launches with rays generated in-kernel and frames kept on device.
+"""
+import copy
+import ctypes
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _capi
+from .config import GridLayout, cascade_count
+
+
+# ------------------------------------------------------------------------------------------------ small modules
+class _MLPWeights(nn.Module):
+    """Parameter container with the reference's key layout `net.{i}.weight` (cond_encoder.py:183-195, bias-free)."""
+
+    def __init__(self, dim_in, dim_out, dim_hidden, num_layers):
+        super().__init__()
+        self.net = nn.ModuleList([
+            nn.Linear(dim_in if l == 0 else dim_hidden, dim_out if l == num_layers - 1 else dim_hidden, bias=False)
+            for l in range(num_layers)])
+
+
+class _GridParams(nn.Module):
+    """`embeddings` + `offsets` exactly like GridEncoder (gridencoder/grid.py:98-143)."""
+
+    def __init__(self, layout: GridLayout):
+        super().__init__()
+        self.layout = layout
+        self.register_buffer("offsets", torch.from_numpy(layout.offsets.copy()))
+        self.embeddings = nn.Parameter(torch.empty(layout.n_entries, layout.level_dim).uniform_(-1e-4, 1e-4))
+
+
+class _AudioNet(nn.Module):
+    """cond_encoder.py:98-143 for win_size == 1 (all strides 1)."""
+
+    def __init__(self, dim_in, dim_aud):
+        super().__init__()
+        self.encoder_conv = nn.Sequential(
+            nn.Conv1d(dim_in, 32, 3, 1, 1), nn.LeakyReLU(0.02, True), nn.Conv1d(32, 32, 3, 1, 1), nn.LeakyReLU(0.02, True),
+            nn.Conv1d(32, 64, 3, 1, 1), nn.LeakyReLU(0.02, True), nn.Conv1d(64, 64, 3, 1, 1), nn.LeakyReLU(0.02, True))
+        self.encoder_fc1 = nn.Sequential(nn.Linear(64, 64), nn.LeakyReLU(0.02, True), nn.Linear(64, dim_aud))
+
+    def forward(self, x):  # [b, t=1, c]
+        x = self.encoder_conv(x.permute(0, 2, 1)).squeeze(-1)
+        return self.encoder_fc1(x)
+
+
+class _AudioAttNet(nn.Module):
+    """cond_encoder.py:146-180; also a batched variant over frames."""
+
+    def __init__(self, dim, seq_len):
+        super().__init__()
+        self.seq_len, self.in_out_dim = seq_len, dim
+        self.attentionConvNet = nn.Sequential(
+            nn.Conv1d(dim, 16, 3, 1, 1), nn.LeakyReLU(0.02, True), nn.Conv1d(16, 8, 3, 1, 1), nn.LeakyReLU(0.02, True),
+            nn.Conv1d(8, 4, 3, 1, 1), nn.LeakyReLU(0.02, True), nn.Conv1d(4, 2, 3, 1, 1), nn.LeakyReLU(0.02, True),
+            nn.Conv1d(2, 1, 3, 1, 1), nn.LeakyReLU(0.02, True))
+        self.attentionNet = nn.Sequential(nn.Linear(seq_len, seq_len), nn.Softmax(dim=1))
+
+    def forward(self, x):  # [seq, c] -> [c]
+        return self.forward_batched(x.unsqueeze(0))[0]
+
+    def forward_batched(self, x):  # [T, seq, c] -> [T, c]
+        y = self.attentionConvNet(x[..., :self.in_out_dim].permute(0, 2, 1))  # [T,1,seq]
+        y = self.attentionNet(y.view(-1, self.seq_len)).unsqueeze(-1)         # [T,seq,1]
+        return torch.sum(y * x, dim=1)
+
+
+# ------------------------------------------------------------------------------------------------ head model
+class RADNeRF(nn.Module):
+    has_torso = False
+
+    def __init__(self, hparams):
+        super().__init__()
+        self.hparams = copy.deepcopy(hparams)
+        hp = self.hparams
+        if not hp.get("cuda_ray", True):
+            raise NotImplementedError("only the cuda_ray path exists (as in the reference)")
+        # --- NeRFRenderer.__init__ (modules/radnerfs/renderer.py:66-102)
+        self.bound = hp["bound"]
+        self.cascade = cascade_count(hp["bound"])
+        self.grid_size = hp["grid_size"]
+        self.density_scale = 1
+        self.min_near = hp["min_near"]
+        self.density_thresh = hp["density_thresh"]
+        b = float(self.bound)
+        aabb = torch.tensor([-b, -b / 2, -b, b, b / 2, b], dtype=torch.float32)
+        self.register_buffer("aabb_train", aabb.clone())
+        self.register_buffer("aabb_infer", aabb.clone())
+        self.individual_embedding_num = hp["individual_embedding_num"]
+        self.individual_embedding_dim = hp["individual_embedding_dim"]
+        if self.individual_embedding_dim > 0:
+            self.individual_embeddings = nn.Parameter(torch.randn(self.individual_embedding_num, self.individual_embedding_dim) * 0.1)
+        self.register_buffer("density_grid", torch.zeros([self.cascade, self.grid_size ** 3]))
+        self.register_buffer("density_bitfield", torch.zeros(self.cascade * self.grid_size ** 3 // 8, dtype=torch.uint8))
+        self.register_buffer("step_counter", torch.zeros(16, 2, dtype=torch.int32))
+        # --- RADNeRF.__init__ (modules/radnerfs/radnerf.py:14-86)
+        if hp["cond_type"] == "esperanto":
+            self.cond_in_dim = 44
+        elif hp["cond_type"] == "deepspeech":
+            self.cond_in_dim = 29
+        elif hp["cond_type"] == "idexp_lm3d_normalized":
+            self.cond_in_dim = {"lm68": 68 * 3, "lm131": 131 * 3, "lm468": 468 * 3}[hp.get("nerf_keypoint_mode", "lm68")]
+        else:
+            raise NotImplementedError()
+        if hp.get("add_eye_blink_cond", False):
+            raise NotImplementedError("add_eye_blink_cond belongs to the SR configs (SURVEY.md 8(f) rank 2)")
+        self.cond_out_dim = hp["cond_out_dim"] // 2 * 2
+        self.cond_win_size = hp["cond_win_size"]
+        self.smo_win_size = hp["smo_win_size"]
+        if self.cond_win_size != 1:
+            raise NotImplementedError("cond_win_size != 1 (audio-window conditioning) is not on the May path")
+        self.cond_prenet = _AudioNet(self.cond_in_dim, self.cond_out_dim)
+        self.with_att = hp["with_att"]
+        if self.with_att:
+            self.cond_att_net = _AudioAttNet(self.cond_out_dim, self.smo_win_size)
+        gt = {"tiledgrid": "tiled", "hashgrid": "hash"}[hp["grid_type"]]
+        it = hp["grid_interpolation_type"]
+        self.position_embedder = _GridParams(GridLayout(3, log2_hashmap_size=hp["log2_hashmap_size"], desired_resolution=hp["desired_resolution"] * self.bound, gridtype=gt, interpolation=it))
+        self.ambient_coord_dim = hp["ambient_coord_dim"]
+        self.ambient_net = _MLPWeights(32 + self.cond_out_dim, self.ambient_coord_dim, hp["hidden_dim_ambient"], hp["num_layers_ambient"])
+        self.ambient_embedder = _GridParams(GridLayout(self.ambient_coord_dim, log2_hashmap_size=hp["log2_hashmap_size"], desired_resolution=hp["desired_resolution"], gridtype=gt, interpolation=it))
+        self.geo_feat_dim = hp["geo_feat_dim"]
+        self.sigma_net = _MLPWeights(32 + 32, 1 + self.geo_feat_dim, hp["hidden_dim_sigma"], hp["num_layers_sigma"])
+        self.color_net = _MLPWeights(16 + self.geo_feat_dim + self.individual_embedding_dim, 3, hp["hidden_dim_color"], hp["num_layers_color"])
+        shape_ok = (hp["hidden_dim_ambient"] == 128 and hp["num_layers_ambient"] == 3 and hp["hidden_dim_sigma"] == 128 and
+                    hp["num_layers_sigma"] == 3 and hp["geo_feat_dim"] == 128 and hp["hidden_dim_color"] == 128 and
+                    hp["num_layers_color"] == 2 and self.cond_out_dim == 64 and self.ambient_coord_dim in (2, 3))
+        if not shape_ok:
+            raise NotImplementedError("libgfpp kernels are built for the May architecture (hidden 128, 3/3/2 layers, cond 64)")
+        self._packed = None  # (key, packed_dev, Model, keepalive)
+        self._workspace = None
+
+    # ------------------------------------------------------------------ state invalidation
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        self._workspace = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._packed = None
+        return super().load_state_dict(*a, **k)
+
+    def invalidate(self):
+        """Call after mutating parameters in place (the packed, transposed copies are rebuilt lazily)."""
+        self._packed = None
+
+    # ------------------------------------------------------------------ conditioning (plumbing, PyTorch)
+    def cal_cond_feat(self, cond, eye_area_percent=None):
+        """radnerf.py:88-106.  cond: [smo_win, 1, C] -> [64]."""
+        with torch.autocast("cuda", enabled=False):
+            feat = self.cond_prenet(cond.float())
+            if self.with_att:
+                feat = self.cond_att_net(feat)
+        return feat
+
+    def cal_cond_feat_clip(self, cond_seq):
+        """All frames at once: cond_seq [T,1,C] -> [T,64]; windows as get_audio_features(att_mode=2)
+        (modules/radnerfs/utils.py:86-102: centred, zero-padded)."""
+        with torch.autocast("cuda", enabled=False):
+            T = cond_seq.shape[0]
+            S = self.smo_win_size
+            left = S // 2
+            x = cond_seq.float().reshape(T, -1)
+            pad = torch.zeros(left, x.shape[1], device=x.device, dtype=x.dtype)
+            padr = torch.zeros(S - left - 1, x.shape[1], device=x.device, dtype=x.dtype)
+            xp = torch.cat([pad, x, padr], 0)
+            idx = torch.arange(T, device=x.device).unsqueeze(1) + torch.arange(S, device=x.device).unsqueeze(0)
+            wins = xp[idx]                                                  # [T,S,C]
+            feat = self.cond_prenet(wins.reshape(T * S, 1, -1)).view(T, S, -1)
+            # the reference zero-pads the *window*, and the prenet maps a zero row to f(0) != 0: same here
+            if self.with_att:
+                feat = self.cond_att_net.forward_batched(feat)
+            else:
+                feat = feat[:, left]
+        return feat
+
+    # ------------------------------------------------------------------ packing
+    def _grid_desc(self, gp: _GridParams, keep):
+        lay = gp.layout
+        d = _capi.GridDesc()
+        emb = gp.embeddings.detach()
+        if emb.dtype != torch.float32 or not emb.is_contiguous():
+            emb = emb.float().contiguous()
+        keep.append(emb)
+        off = np.ascontiguousarray(gp.offsets.detach().cpu().numpy().astype(np.int32))
+        keep.append(off)
+        d.embeddings = emb.data_ptr()
+        d.offsets_host = off.ctypes.data
+        d.input_dim = lay.input_dim
+        d.num_levels = lay.num_levels
+        d.base_resolution = lay.base_resolution
+        d.log2_per_level_scale = float(lay.S)
+        d.gridtype = lay.gridtype_id
+        d.interp = lay.interp_id
+        d.align_corners = int(lay.align_corners)
+        return d
+
+    def _w(self, t, keep):
+        t = t.detach()
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.float().contiguous()
+        keep.append(t)
+        return t.data_ptr()
+
+    def _fill_desc(self, d, keep):
+        d.position_grid = self._grid_desc(self.position_embedder, keep)
+        d.ambient_grid = self._grid_desc(self.ambient_embedder, keep)
+        for i in range(3):
+            d.ambient_w[i] = self._w(self.ambient_net.net[i].weight, keep)
+            d.sigma_w[i] = self._w(self.sigma_net.net[i].weight, keep)
+        for i in range(2):
+            d.color_w[i] = self._w(self.color_net.net[i].weight, keep)
+        d.cond_dim = self.cond_out_dim
+        d.ind_dim = self.individual_embedding_dim
+        if self.individual_embedding_dim > 0:
+            # eval uses individual_embeddings[0] (renderer.py:313-315)
+            d.individual_code = self._w(self.individual_embeddings[0], keep)
+        bf = self.density_bitfield
+        keep.append(bf)
+        d.density_bitfield = bf.data_ptr()
+        aabb = self.aabb_infer.detach().cpu().tolist()
+        for i in range(6):
+            d.aabb[i] = aabb[i]
+        d.bound = float(self.bound)
+        d.min_near = float(self.min_near)
+        d.cascade = self.cascade
+        d.grid_size = self.grid_size
+        d.density_scale = float(self.density_scale)
+        d.has_torso = 0
+
+    def _ensure_packed(self):
+        dev = self.density_bitfield.device
+        if dev.type != "cuda":
+            raise _capi.GfppError("model is not on a CUDA device: libgfpp has no CPU path (call .cuda())")
+        key = (float(self.density_scale), getattr(self, "mean_density_torso", None), dev.index)
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed
+        L = _capi.lib()
+        with torch.cuda.device(dev):
+            _capi.check(L.gfpp_check_device(), "gfpp_check_device")
+            keep = []
+            d = _capi.ModelDesc()
+            self._fill_desc(d, keep)
+            nbytes = L.gfpp_model_packed_bytes(ctypes.byref(d))
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            model = _capi.Model()
+            _capi.check(L.gfpp_model_pack(ctypes.byref(d), packed.data_ptr(), nbytes, ctypes.byref(model), _capi.stream_ptr(dev)),
+                        "gfpp_model_pack")
+        self._packed = (key, packed, model, keep)
+        return self._packed
+
+    # ------------------------------------------------------------------ core call
+    def render_frames(self, cond_feat, *, rays_o=None, rays_d=None, poses_c2w=None, intrinsics=None, H=None, W=None,
+                      pose6=None, bg_coords=None, bg_color=None, dt_gamma=0.0, max_steps=1024, T_thresh=1e-4,
+                      want_torso_maps=True, want_stats=False):
+        """Render F frames with one call into libgfpp.  Returns a dict of device tensors with a leading F axis.
+
+        Either (rays_o, rays_d) [F,N,3] or (poses_c2w [F,4,4], intrinsics, H, W) must be given."""
+        if self.training:
+            raise NotImplementedError("libgfpp implements the inference branch only (renderer.py:340-384)")
+        _, packed, model, _keep = self._ensure_packed()
+        dev = self.density_bitfield.device
+        L = _capi.lib()
+        f32 = torch.float32
+        cond_feat = cond_feat.to(dev, f32).reshape(-1, self.cond_out_dim).contiguous()
+        Fn = cond_feat.shape[0]
+        fr = _capi.Frames()
+        hold = [cond_feat]
+        if rays_o is not None:
+            rays_o = rays_o.to(dev, f32).reshape(Fn, -1, 3).contiguous()
+            rays_d = rays_d.to(dev, f32).reshape(Fn, -1, 3).contiguous()
+            N = rays_o.shape[1]
+            fr.rays_o, fr.rays_d = rays_o.data_ptr(), rays_d.data_ptr()
+            hold += [rays_o, rays_d]
+        else:
+            poses_c2w = poses_c2w.to(dev, f32).reshape(Fn, 16).contiguous()
+            N = H * W
+            fr.poses_c2w = poses_c2w.data_ptr()
+            fr.fx, fr.fy, fr.cx, fr.cy = [float(v) for v in intrinsics]
+            fr.img_h, fr.img_w = H, W
+            hold.append(poses_c2w)
+        fr.n_frames, fr.n_rays = Fn, N
+        fr.cond_feat = cond_feat.data_ptr()
+        if self.has_torso:
+            pose6 = pose6.to(dev, f32).reshape(Fn, 6).contiguous()
+            bg_coords = bg_coords.to(dev, f32).reshape(N, 2).contiguous()
+            fr.torso_pose6, fr.bg_coords = pose6.data_ptr(), bg_coords.data_ptr()
+            hold += [pose6, bg_coords]
+        if bg_color is not None:
+            if not torch.is_tensor(bg_color):
+                bg_color = torch.full((N, 3), float(bg_color), device=dev, dtype=f32)
+            bg_color = bg_color.to(dev, f32).reshape(-1, 3)
+            if bg_color.shape[0] == 1:
+                bg_color = bg_color.expand(N, 3)
+            bg_color = bg_color.contiguous()
+            fr.bg_color = bg_color.data_ptr()
+            hold.append(bg_color)
+        fr.dt_gamma, fr.max_steps, fr.T_thresh = float(dt_gamma), int(max_steps), float(T_thresh)
+
+        out = _capi.Outputs()
+        res = {"rgb_map": torch.empty(Fn, N, 3, device=dev, dtype=f32), "depth_map": torch.empty(Fn, N, device=dev, dtype=f32),
+               "weights_sum": torch.empty(Fn, N, device=dev, dtype=f32)}
+        out.rgb_map, out.depth_map, out.weights_sum = res["rgb_map"].data_ptr(), res["depth_map"].data_ptr(), res["weights_sum"].data_ptr()
+        if self.has_torso and want_torso_maps:
+            res["torso_alpha_map"] = torch.empty(Fn, N, device=dev, dtype=f32)
+            res["torso_rgb_map"] = torch.empty(Fn, N, 3, device=dev, dtype=f32)
+            res["deform"] = torch.empty(Fn, N, 2, device=dev, dtype=f32)
+            out.torso_alpha_map, out.torso_rgb_map, out.torso_deform = (res["torso_alpha_map"].data_ptr(), res["torso_rgb_map"].data_ptr(), res["deform"].data_ptr())
+        if want_stats:
+            res["stats"] = torch.empty(Fn, 4, device=dev, dtype=torch.int32)
+            out.stats = res["stats"].data_ptr()
+        need = L.gfpp_render_workspace_bytes(Fn, N, int(max_steps))
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _capi.check(L.gfpp_render_frames(ctypes.byref(model), ctypes.byref(fr), ctypes.byref(out), self._workspace.data_ptr(),
+                                             self._workspace.numel(), _capi.stream_ptr(dev)), "gfpp_render_frames")
+        self.last_launch_count = int(L.gfpp_last_launch_count())
+        del hold
+        return res
+
+    # ------------------------------------------------------------------ the reference's render()
+    @torch.no_grad()
+    def render(self, rays_o, rays_d, cond, bg_coords, poses, index=0, dt_gamma=0, bg_color=None, perturb=False,
+               force_all_rays=False, max_steps=1024, T_thresh=1e-4, cond_mask=None, eye_area_percent=None, **kwargs):
+        if perturb:
+            raise NotImplementedError("perturb=True is a training/GUI option; the inference driver passes False")
+        if cond_mask is not None:
+            raise NotImplementedError("cond_mask is unused by the May configs")
+        prefix = rays_o.shape[:-1]
+        if rays_o.numel() // 3 != int(np.prod(prefix)) or (len(prefix) > 1 and prefix[0] != 1):
+            raise ValueError("render() assumes B == 1 (renderer.py:287)")
+        cond_feat = self.cal_cond_feat(cond.to(self.density_bitfield.device), eye_area_percent=eye_area_percent)
+        res = self.render_frames(cond_feat.reshape(1, -1), rays_o=rays_o.reshape(1, -1, 3), rays_d=rays_d.reshape(1, -1, 3),
+                                 pose6=poses if self.has_torso else None, bg_coords=bg_coords if self.has_torso else None,
+                                 bg_color=bg_color, dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh)
+        results = {"depth_map": res["depth_map"].view(*prefix), "rgb_map": res["rgb_map"].view(*prefix, 3),
+                   "weights_sum": res["weights_sum"].view(-1)}
+        if self.has_torso:
+            alpha = res["torso_alpha_map"].view(-1, 1)
+            results["torso_alpha_map"] = alpha
+            trgb = res["torso_rgb_map"].view(-1, 3)
+            results["torso_rgb_map"] = trgb.view(1, -1, 3) if (bg_color is not None and torch.is_tensor(bg_color) and bg_color.dim() == 3) else trgb
+            mask = self.torso_mask(bg_coords)
+            if bool(mask.any()):
+                results["deform"] = res["deform"].view(-1, 2)[mask]
+        return results
+
+    # ------------------------------------------------------------------ clip API
+    @torch.no_grad()
+    def render_clip(self, poses_c2w, intrinsics, H, W, cond_seq=None, cond_feat=None, bg_color=None, bg_coords=None, pose6=None,
+                    dt_gamma=None, max_steps=None, T_thresh=1e-2, frames_per_call=64, out=None, want_stats=False):
+        """Render a clip: poses_c2w [T,4,4], cond_seq [T,1,C] (or precomputed cond_feat [T,64]).
+        Returns rgb [T,H*W,3] on the model's device (fp32, clamped to [0,1])."""
+        dev = self.density_bitfield.device
+        T = poses_c2w.shape[0]
+        hp = self.hparams
+        dt_gamma = hp["dt_gamma"] if dt_gamma is None else dt_gamma
+        max_steps = hp["max_steps"] if max_steps is None else max_steps
+        if cond_feat is None:
+            cond_feat = self.cal_cond_feat_clip(cond_seq.to(dev))
+        poses_c2w = poses_c2w.to(dev, torch.float32)
+        if self.has_torso and pose6 is None:
+            from .scene import convert_poses
+            pose6 = convert_poses(poses_c2w.cpu()).to(dev)
+        N = H * W
+        rgb = out if out is not None else torch.empty(T, N, 3, device=dev, dtype=torch.float32)
+        stats = []
+        for s in range(0, T, frames_per_call):
+            e = min(T, s + frames_per_call)
+            res = self.render_frames(cond_feat[s:e], poses_c2w=poses_c2w[s:e], intrinsics=intrinsics, H=H, W=W,
+                                     pose6=pose6[s:e] if self.has_torso else None, bg_coords=bg_coords, bg_color=bg_color,
+                                     dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh, want_torso_maps=False,
+                                     want_stats=want_stats)
+            rgb[s:e].copy_(res["rgb_map"])
+            if want_stats:
+                stats.append(res["stats"])
+        if want_stats:
+            return rgb, torch.cat(stats, 0)
+        return rgb
+
+
+# ------------------------------------------------------------------------------------------------ torso model
+class RADNeRFTorso(RADNeRF):
+    has_torso = True
+
+    def __init__(self, hparams):
+        super().__init__(hparams)
+        hp = self.hparams
+        if hp.get("torso_head_aware", False):
+            raise NotImplementedError("torso_head_aware belongs to the SR configs (SURVEY.md 8(f) rank 3)")
+        # radnerf_torso.py:18-49
+        self.register_buffer("density_grid_torso", torch.zeros([self.grid_size ** 2]))
+        self.mean_density_torso = 0
+        self.density_thresh_torso = hp["density_thresh_torso"]
+        self.torso_shrink = hp["torso_shrink"]
+        self.torso_individual_embedding_num = hp["individual_embedding_num"]
+        self.torso_individual_embedding_dim = hp["torso_individual_embedding_dim"]
+        if self.torso_individual_embedding_dim > 0:
+            self.torso_individual_codes = nn.Parameter(torch.randn(self.torso_individual_embedding_num, self.torso_individual_embedding_dim) * 0.1)
+        self.torso_embedder = _GridParams(GridLayout(2, log2_hashmap_size=16, desired_resolution=2048, gridtype="tiled"))
+        din = (2 + 2 * 2 * 10) + (6 + 6 * 2 * 4) + self.torso_individual_embedding_dim
+        self.torso_deform_net = _MLPWeights(din, 2, 64, 3)
+        self.torso_canonicial_net = _MLPWeights(32 + din, 4, 32, 3)
+
+    def _fill_desc(self, d, keep):
+        super()._fill_desc(d, keep)
+        d.has_torso = 1
+        d.torso_grid = self._grid_desc(self.torso_embedder, keep)
+        for i in range(3):
+            d.torso_deform_w[i] = self._w(self.torso_deform_net.net[i].weight, keep)
+            d.torso_canon_w[i] = self._w(self.torso_canonicial_net.net[i].weight, keep)
+        d.torso_code_dim = self.torso_individual_embedding_dim
+        if self.torso_individual_embedding_dim > 0:
+            d.torso_code = self._w(self.torso_individual_codes[0], keep)  # radnerf_torso.py:160-162
+        g = self.density_grid_torso
+        keep.append(g)
+        d.density_grid_torso = g.data_ptr()
+        # mean_density_torso is a plain attribute that is NOT in the checkpoint (=> 0 after load, radnerf_torso.py:22,167)
+        d.density_thresh_torso = float(min(self.density_thresh_torso, self.mean_density_torso))
+        d.torso_shrink = float(self.torso_shrink)
+
+    def torso_mask(self, bg_coords):
+        """radnerf_torso.py:166-169 (host-side helper used only to shape the `deform` result like the reference)."""
+        G = self.grid_size
+        thr = min(self.density_thresh_torso, self.mean_density_torso)
+        occ = F.grid_sample(self.density_grid_torso.view(1, 1, G, G), bg_coords.to(self.density_grid_torso.device).float().view(1, -1, 1, 2), align_corners=True).view(-1)
+        return occ > thr

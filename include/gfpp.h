@@ -1,0 +1,194 @@
+/*
+ * gfpp.h -- C-ABI of libgfpp.so: the B200 (sm_100a) render hot path of GeneFace++.
+ *
+ * Drop-in boundary.  Plain pointers and sizes only; no torch types.
+ * All pointers are DEVICE pointers unless the name ends in _host.  Every call is
+ * stream-ordered on `stream` (a cudaStream_t passed as void*), never synchronises the
+ * device, never allocates device memory (callers provide packed-model and workspace
+ * buffers whose sizes they query first) and never throws: the return value is 0 on success
+ * or a negative gfpp_status; gfpp_last_error() returns a thread-local message.
+ *
+ * Two levels are exported.
+ *
+ *  (A) per-op entry points that mirror, argument for argument, the pybind functions of the
+ *      reference's four CUDA extensions, so the reference's own Python wrappers can bind them
+ *      (INTEGRATION.md shows the stub):
+ *        gfpp_near_far_from_aabb   <- modules/radnerfs/raymarching/src/raymarching.h:7  (raymarching.cu:148-156)
+ *        gfpp_march_rays           <- raymarching.h:19 (raymarching.cu:932-939)
+ *        gfpp_composite_rays       <- raymarching.h:20 (raymarching.cu:1032-1037)
+ *        gfpp_grid_encode_forward  <- modules/radnerfs/encoders/gridencoder/src/gridencoder.h:12 (gridencoder.cu:446-471)
+ *        gfpp_sh_encode_forward    <- modules/radnerfs/encoders/shencoder/src/shencoder.h:9 (shencoder.cu:400)
+ *        gfpp_freq_encode_forward  <- modules/radnerfs/encoders/freqencoder/src/freqencoder.h:7 (freqencoder.cu:97-110)
+ *
+ *  (B) the fused frame renderer that replaces the whole host-driven loop of
+ *      NeRFRenderer.render / RADNeRFTorso.render (modules/radnerfs/renderer.py:340-399,
+ *      modules/radnerfs/radnerf_torso.py:129-197) for one or many frames per call:
+ *        gfpp_model_packed_bytes / gfpp_model_pack / gfpp_render_workspace_bytes / gfpp_render_frames
+ */
+#ifndef GFPP_H_
+#define GFPP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFPP_API __attribute__((visibility("default")))
+
+typedef enum {
+    GFPP_OK = 0,
+    GFPP_ERR_INVALID = -1,     /* bad argument (null pointer, unsupported C/D/degree, size mismatch) */
+    GFPP_ERR_CUDA = -2,        /* a CUDA runtime call failed; see gfpp_last_error() */
+    GFPP_ERR_WORKSPACE = -3,   /* caller-provided buffer too small */
+    GFPP_ERR_UNSUPPORTED = -4  /* configuration outside what the kernels were built for */
+} gfpp_status;
+
+GFPP_API const char *gfpp_last_error(void);
+GFPP_API int gfpp_version(void);
+/* device check: returns GFPP_OK iff the current device is compute capability 10.x */
+GFPP_API int gfpp_check_device(void);
+
+/* ------------------------------------------------------------------ (A) per-op mirror */
+
+/* nears/fars [N] <- slab test of rays [N,3] against aabb[6]; miss => both FLT_MAX; near >= min_near */
+GFPP_API int gfpp_near_far_from_aabb(const float *rays_o, const float *rays_d, const float *aabb, uint32_t N,
+                                     float min_near, float *nears, float *fars, void *stream);
+
+/* one round of inference marching: for each of n_alive rays emit up to n_step occupied samples.
+ * xyzs/dirs [M,3] and deltas [M,2] must be zero-initialised by the caller (as the reference wrapper does). */
+GFPP_API int gfpp_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t,
+                             const float *rays_o, const float *rays_d, float bound, float dt_gamma,
+                             uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t *grid, const float *nears,
+                             const float *fars, float *xyzs, float *dirs, float *deltas, const float *noises,
+                             void *stream);
+
+/* front-to-back compositing of one round, in place; kills rays by writing -1 into rays_alive */
+GFPP_API int gfpp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive,
+                                 float *rays_t, const float *sigmas, const float *rgbs, const float *deltas,
+                                 float *weights_sum, float *depth, float *image, void *stream);
+
+/* multi-resolution grid encode, forward only.  inputs [B,D] in [0,1]; embeddings [sum,C] fp32;
+ * offsets_host [L+1] (HOST pointer: the level layout is tiny and static); outputs [L,B,C] (L-major,
+ * exactly what the reference kernel writes).  D in {2,3}, C == 2 (the only shapes on the path). */
+GFPP_API int gfpp_grid_encode_forward(const float *inputs, const float *embeddings, const int32_t *offsets_host,
+                                      float *outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                                      uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp, void *stream);
+
+/* real spherical harmonics, degree (called C in the reference) 1..4: outputs [B, degree^2] */
+GFPP_API int gfpp_sh_encode_forward(const float *inputs, float *outputs, uint32_t B, uint32_t D, uint32_t degree,
+                                    void *stream);
+
+/* [x, sin(2^f x), sin(2^f x + pi/2)]_f : outputs [B, C], C = D + 2*D*deg */
+GFPP_API int gfpp_freq_encode_forward(const float *inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C,
+                                      float *outputs, void *stream);
+
+/* ------------------------------------------------------------------ (B) fused renderer */
+
+/* One multi-resolution grid in the reference layout (GridEncoder, grid.py:98-136). */
+typedef struct {
+    const float *embeddings;      /* device [n_entries, 2] fp32 */
+    const int32_t *offsets_host;  /* host   [num_levels+1] */
+    uint32_t input_dim;           /* 2 or 3 */
+    uint32_t num_levels;          /* <= 16 */
+    uint32_t base_resolution;     /* H (16) */
+    float log2_per_level_scale;   /* S, as float32(log2(per_level_scale)) */
+    uint32_t gridtype;            /* 0 hash, 1 tiled */
+    uint32_t interp;              /* 0 linear, 1 smoothstep */
+    int align_corners;
+} gfpp_grid_desc;
+
+/* Weights in the reference's nn.Linear layout [out, in], fp32, device pointers (state_dict tensors). */
+typedef struct {
+    /* head field (modules/radnerfs/radnerf.py:56-86) */
+    gfpp_grid_desc position_grid;       /* 3-D */
+    gfpp_grid_desc ambient_grid;        /* ambient_coord_dim-D (3 for the May configs) */
+    const float *ambient_w[3];          /* (128,96) (128,128) (3,128) */
+    const float *sigma_w[3];            /* (128,64) (128,128) (129,128) */
+    const float *color_w[2];            /* (128,148) (3,128) */
+    const float *individual_code;       /* [ind_dim] = individual_embeddings[0]; may be NULL if ind_dim == 0 */
+    uint32_t cond_dim;                  /* 64 */
+    uint32_t ind_dim;                   /* 4 */
+    /* occupancy + marching (modules/radnerfs/renderer.py:67-102) */
+    const uint8_t *density_bitfield;    /* [cascade * grid_size^3 / 8], Morton order */
+    float aabb[6];
+    float bound;
+    float min_near;
+    uint32_t cascade;
+    uint32_t grid_size;
+    float density_scale;
+    /* torso field (modules/radnerfs/radnerf_torso.py:17-49); has_torso == 0 for head-only RADNeRF */
+    int has_torso;
+    gfpp_grid_desc torso_grid;          /* 2-D */
+    const float *torso_deform_w[3];     /* (64,104) (64,64) (2,64) */
+    const float *torso_canon_w[3];      /* (32,136) (32,32) (4,32) */
+    const float *torso_code;            /* [8] = torso_individual_codes[0] */
+    const float *density_grid_torso;    /* [grid_size^2] */
+    float density_thresh_torso;         /* min(density_thresh_torso, mean_density_torso) as the reference evaluates it */
+    float torso_shrink;
+    uint32_t torso_code_dim;            /* 8 */
+} gfpp_model_desc;
+
+/* Host-side model handle: plain data, caller-allocated (stack, heap, numpy buffer ...), filled by
+ * gfpp_model_pack().  It holds level tables, launch constants and device pointers into `packed` and into
+ * the borrowed tables; copying it is fine, it owns nothing. */
+typedef struct gfpp_model {
+    uint64_t opaque[512];
+} gfpp_model;
+
+/* bytes of the device buffer gfpp_model_pack() fills (repacked/transposed weights, occupancy bounds) */
+GFPP_API size_t gfpp_model_packed_bytes(const gfpp_model_desc *desc);
+/* Repack on `stream` into `packed` (device, >= gfpp_model_packed_bytes) and fill *model.  Weights are copied
+ * (k-major, layer chunks in streaming order); the desc's grid tables, bitfield and density_grid_torso are
+ * BORROWED and must stay alive while the model is used.  Unsupported layer shapes => GFPP_ERR_UNSUPPORTED
+ * (the kernels are built for the May architecture: hidden 128, cond 64, geo 128, 16 levels x 2 features). */
+GFPP_API int gfpp_model_pack(const gfpp_model_desc *desc, void *packed, size_t packed_bytes, gfpp_model *model,
+                             void *stream);
+
+typedef struct {
+    uint32_t n_frames;            /* F */
+    uint32_t n_rays;              /* N = H*W rays per frame */
+    /* rays: either supplied (parity on identical rays) ... */
+    const float *rays_o;          /* [F,N,3] or NULL */
+    const float *rays_d;          /* [F,N,3] or NULL */
+    /* ... or generated in-kernel from the camera (get_rays, modules/radnerfs/utils.py:283-364) */
+    const float *poses_c2w;       /* [F,4,4] row-major; used when rays_o == NULL */
+    float fx, fy, cx, cy;
+    uint32_t img_h, img_w;
+    const float *cond_feat;       /* [F,cond_dim] output of cal_cond_feat (radnerf.py:88-106) */
+    const float *torso_pose6;     /* [F,6] euler+trans from convert_poses; NULL if no torso */
+    const float *bg_coords;       /* [N,2] (shared by all frames); NULL if no torso */
+    const float *bg_color;        /* [N,3] shared by all frames, or NULL => 1.0 (renderer.py:387-388) */
+    float dt_gamma;
+    uint32_t max_steps;
+    float T_thresh;
+} gfpp_frames;
+
+typedef struct {
+    float *rgb_map;               /* [F,N,3] final image (renderer.py:390-397 / radnerf_torso.py:191-197) */
+    float *depth_map;             /* [F,N] */
+    float *weights_sum;           /* [F,N] head alpha */
+    float *torso_alpha_map;       /* [F,N]   or NULL */
+    float *torso_rgb_map;         /* [F,N,3] or NULL (bg mixed with torso, radnerf_torso.py:187-189) */
+    float *torso_deform;          /* [F,N,2] deformation for masked pixels, 0 elsewhere; or NULL */
+    int32_t *stats;               /* [F,4] = {B_total, n_survivors, S_valid_samples, P_torso_pixels} or NULL */
+} gfpp_outputs;
+
+GFPP_API size_t gfpp_render_workspace_bytes(uint32_t n_frames, uint32_t n_rays, uint32_t max_steps);
+/* Enqueue the whole clip (or one frame): pass-1 persistent head kernel, on-device round-schedule
+ * replay, pass-2 for rays that outlive max_steps, torso + composite epilogue.  No host sync. */
+GFPP_API int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *frames, const gfpp_outputs *out,
+                                void *workspace, size_t workspace_bytes, void *stream);
+/* Diagnostics for bench.py's roofline leg: when enabled, gfpp_render_frames records CUDA events (on the launching
+ * stream) around its three main kernels; gfpp_profile_read() waits for those events and returns the durations of the
+ * most recent call in milliseconds: ms[0] = head pass 1, ms[1] = schedule + head pass 2, ms[2] = torso/composite epilogue. */
+GFPP_API int gfpp_profile_enable(int on);
+GFPP_API int gfpp_profile_read(float ms[3]);
+/* number of kernels the last gfpp_render_frames call on this thread launched */
+GFPP_API int gfpp_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFPP_H_ */
