@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--frames-per-call", type=int, default=50)
     ap.add_argument("--cpu-frames", type=int, default=1, help="frames of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("GFPP_BENCH_PRECISION", "fp32"), choices=["fp32", "fp16", "bf16x3", "bf16"],
+                    help="arithmetic of the head MLP GEMMs (marching/gather/compositing are fp32 in every mode)")
     return ap.parse_args()
 
 
@@ -187,6 +189,7 @@ def main():
     model = (RADNeRF if args.head_only else RADNeRFTorso)(sc.hparams)
     model.load_state_dict(sc.state, strict=True)
     model.density_scale = sc.density_scale
+    model.mlp_precision = args.precision
     model = model.to(dev).eval()
     s, e = gdist.frame_block(T * world, rank, world)
     poses_host = torch.stack([sc.pose(t) for t in range(s, e)]).pin_memory()
@@ -283,7 +286,7 @@ def main():
     alg_bytes = Fc * (S_per_frame * 2048 + N * (12 + 4 + 4)) + 0.36e6
     alg_flops = Fc * S_per_frame * 178944
     achieved = alg_bytes / head_t / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_head (pass 1)", "achieved": achieved, "peak": hbm, "peak_source": peak_kind, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_head (pass 1)" if args.precision == "fp32" else "k_head_tc (pass 1)", "achieved": achieved, "peak": hbm, "peak_source": peak_kind, "unit": "GB/s",
                 "frac": achieved / hbm, "traffic": None, "launch_ms": head_t * 1000.0, "frames_per_launch": Fc,
                 "share_of_step": head_t / (head_t + statistics.mean(pass2_ms) / 1000 + statistics.mean(epi_ms) / 1000),
                 "fp32_tflops": alg_flops / head_t / 1e12, "pass2_ms": statistics.mean(pass2_ms), "epilogue_ms": statistics.mean(epi_ms),
@@ -315,8 +318,10 @@ def main():
     if rank == 0:
         line = {"metric": "frames/sec at 512x512 head+torso" if not args.head_only else "frames/sec at 512x512 head", "value": fps,
                 "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args), "frames_per_gpu_per_step": T, "frames_per_call": args.frames_per_call,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "fp16": "f16 operands, f32 accumulate (tcgen05)", "bf16x3": "bf16 hi/lo split x3, f32 accumulate (tcgen05)", "bf16": "bf16 operands, f32 accumulate (tcgen05)"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": workload_name(args), "mlp_precision": args.precision, "frames_per_gpu_per_step": T, "frames_per_call": args.frames_per_call,
                            "S_valid_samples_per_frame": S_per_frame, "P_torso_pixels_per_frame": P_per_frame, "B_total": int(st[0, 0]),
                            "parallelism": f"frame-sharded x{world}, 1 all-gather of uint8 RGB" if world > 1 else "single GPU",
                            "l2": "per-step working set (786 MB fp32 frames out + 1.8 GB workspace) >> 126 MB L2; grid tables (14.4 MB) are L2-resident by design"},

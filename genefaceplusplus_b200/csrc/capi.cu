@@ -22,6 +22,9 @@ cudaError_t launch_grid_encode(const GridMeta &, const float *, const float *, f
 cudaError_t launch_sh_encode(const float *, float *, uint32_t, uint32_t, cudaStream_t);
 cudaError_t launch_freq_encode(const float *, uint32_t, uint32_t, uint32_t, float *, cudaStream_t);
 cudaError_t launch_occupancy_bounds(const uint8_t *, uint32_t, uint32_t, int *, cudaStream_t);
+// tc_pack.cu
+cudaError_t launch_pack_tc_tile(const float *, int, int, int, int, int, int, int, int, unsigned char *, unsigned char *, cudaStream_t);
+cudaError_t launch_tc_selftest(const float *, int, const unsigned char *, const unsigned char *, int, int, int, int, float *, cudaStream_t);
 }  // namespace gfpp
 
 using namespace gfpp;
@@ -104,13 +107,27 @@ struct ModelHost {
     float bound, min_near, density_scale, density_thresh_torso, torso_shrink;
     uint32_t cascade, grid_size;
     int use_occ_box;
+    int mlp_precision;
+    HeadTcArgs tc;
 };
 static_assert(sizeof(ModelHost) <= sizeof(gfpp_model), "gfpp_model opaque storage too small");
 constexpr uint32_t kMagic = 0x67667070u;  // "gfpp"
 
 struct PackedLayout {
-    size_t wide, narrow, wd0, wd1, wd2, wc0, wc1, wc2, occ, total;
+    size_t wide, narrow, wd0, wd1, wd2, wc0, wc1, wc2, occ, tc_hi, tc_lo, tcn_hi, tcn_lo, total;
 };
+
+// tensor-core weight stream: 12 tiles per batch (see head_tc_kernel.cu)
+struct TcChunk { int layer, rows, col0, kc, k16; };
+constexpr TcChunk kTc[HEAD_TC_NCHUNK] = {
+    {0, 128, 0, 64, 0}, {0, 128, 64, 32, 0},     // ambient L0 (K = 96)
+    {1, 128, 0, 64, 0}, {1, 128, 64, 64, 0},     // ambient L1
+    {2, 128, 0, 64, 0},                          // sigma L0 (K = 64)
+    {3, 128, 0, 64, 0}, {3, 128, 64, 64, 0},     // sigma L1
+    {4, 144, 0, 64, 0}, {4, 144, 64, 64, 0},     // sigma L2: rows 0..127 geo, row 128 sigma, rest zero
+    {5, 128, 16, 64, 0}, {5, 128, 80, 64, 0},    // color L0, geo columns 16..143
+    {5, 128, 0, 16, 1}};                         // color L0, SH columns 0..15 (K16 tile)
+inline int tc_chunk_bytes(int c) { return kTc[c].rows * (kTc[c].k16 ? 32 : 128); }
 
 PackedLayout packed_layout() {
     PackedLayout L;
@@ -127,6 +144,12 @@ PackedLayout packed_layout() {
     L.wc1 = take(32 * 32);
     L.wc2 = take(4 * 32);
     L.occ = take(8);
+    size_t tcb = 0;
+    for (int c = 0; c < HEAD_TC_NCHUNK; ++c) tcb += (size_t)tc_chunk_bytes(c);
+    L.tc_hi = take(tcb / 4);
+    L.tc_lo = take(tcb / 4);
+    L.tcn_hi = take(4 * 2048 / 4);
+    L.tcn_lo = take(4 * 2048 / 4);
     L.total = o;
     return L;
 }
@@ -277,6 +300,28 @@ int gfpp_freq_encode_forward(const float *inputs, uint32_t B, uint32_t D, uint32
     return GFPP_OK;
 }
 
+int gfpp_tc_selftest(const float *A, const float *W, uint32_t N, uint32_t K, int k16_tail, int precision, void *scratch,
+                     float *out, void *stream) {
+    if (!A || !W || !scratch || !out) return fail(GFPP_ERR_INVALID, "tc_selftest: null pointer%s");
+    const int k64 = (int)K - (k16_tail ? 16 : 0);
+    if (N % 16 || N < 16 || N > 144 || k64 <= 0 || k64 % 16 || K > 144 || precision < 1 || precision > 3)
+        return fail(GFPP_ERR_INVALID, "tc_selftest: unsupported shape%s");
+    const int nt64 = (k64 + 63) / 64;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char *hi = (unsigned char *)scratch, *lo = hi + 3 * 18432;
+    const int bf16 = precision != 1;
+    g_launches = 0;
+    CKN(cudaMemsetAsync(scratch, 0, 6 * 18432, st));
+    for (int t = 0; t < nt64; ++t) {
+        const int kc = (k64 - t * 64) < 64 ? (k64 - t * 64) : 64;
+        CK(launch_pack_tc_tile(W, (int)K, 0, t * 64, (int)N, kc, 0, 0, bf16, hi + t * 18432, precision == 2 ? lo + t * 18432 : nullptr, st));
+    }
+    if (k16_tail)
+        CK(launch_pack_tc_tile(W, (int)K, 0, k64, (int)N, 16, 0, 1, bf16, hi + nt64 * 18432, precision == 2 ? lo + nt64 * 18432 : nullptr, st));
+    CK(launch_tc_selftest(A, (int)K, hi, lo, (int)N, nt64, k16_tail, precision, out, st));
+    return GFPP_OK;
+}
+
 // ------------------------------------------------------------------ (B) fused renderer
 size_t gfpp_model_packed_bytes(const gfpp_model_desc *desc) {
     (void)desc;
@@ -356,6 +401,38 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
     const uint32_t H3 = d->grid_size * d->grid_size * d->grid_size;
     CK(launch_occupancy_bounds(d->density_bitfield, d->cascade * H3 / 8, H3, occ, st));
     m.occ_bounds = occ;
+
+    m.mlp_precision = (int)d->mlp_precision;
+    if (d->mlp_precision > 3) return fail(GFPP_ERR_UNSUPPORTED, "model_pack: mlp_precision must be 0..3%s");
+    if (d->mlp_precision != 0) {
+        const int bf16 = d->mlp_precision != 1;
+        const bool split = d->mlp_precision == 2;
+        unsigned char *thi = (unsigned char *)(base + L.tc_hi), *tlo = (unsigned char *)(base + L.tc_lo);
+        unsigned char *nhi = (unsigned char *)(base + L.tcn_hi), *nlo = (unsigned char *)(base + L.tcn_lo);
+        CKN(cudaMemsetAsync(base + L.tc_hi, 0, L.total - L.tc_hi, st));
+        const float *lw[6] = {d->ambient_w[0], d->ambient_w[1], d->sigma_w[0], d->sigma_w[1], d->sigma_w[2], d->color_w[0]};
+        const int lld[6] = {96, 128, 64, 128, 128, col0_in};
+        int boff = 0;
+        for (int c = 0; c < HEAD_TC_NCHUNK; ++c) {
+            const TcChunk &k = kTc[c];
+            m.tc.chunk_off[c] = boff;
+            m.tc.chunk_bytes[c] = tc_chunk_bytes(c);
+            m.tc.chunk_ksteps[c] = k.k16 ? 1 : k.kc / 16;
+            m.tc.chunk_k16[c] = k.k16;
+            if (k.layer == 4) {  // sigma L2: geo rows (W rows 1..128) first, the sigma row (W row 0) as row 128
+                CK(launch_pack_tc_tile(lw[4], 128, 1, k.col0, 128, k.kc, 0, 0, bf16, thi + boff, split ? tlo + boff : nullptr, st));
+                CK(launch_pack_tc_tile(lw[4], 128, 0, k.col0, 1, k.kc, 128, 0, bf16, thi + boff, split ? tlo + boff : nullptr, st));
+            } else {
+                CK(launch_pack_tc_tile(lw[k.layer], lld[k.layer], 0, k.col0, 128, k.kc, 0, k.k16, bf16, thi + boff, split ? tlo + boff : nullptr, st));
+            }
+            boff += tc_chunk_bytes(c);
+        }
+        for (int kt = 0; kt < 2; ++kt) {
+            CK(launch_pack_tc_tile(d->ambient_w[2], 128, 0, kt * 64, amb_dim, 64, 0, 0, bf16, nhi + kt * 2048, split ? nlo + kt * 2048 : nullptr, st));
+            CK(launch_pack_tc_tile(d->color_w[1], 128, 0, kt * 64, 3, 64, 0, 0, bf16, nhi + (2 + kt) * 2048, split ? nlo + (2 + kt) * 2048 : nullptr, st));
+        }
+        m.tc.w_hi = thi; m.tc.w_lo = tlo; m.tc.narrow_hi = nhi; m.tc.narrow_lo = nlo;
+    }
 
     m.has_torso = d->has_torso;
     if (d->has_torso) {
@@ -462,12 +539,14 @@ int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfp
     a.pass = 1;
     a.cursor = counters + 0;
     if (g_profile) CKN(cudaEventRecord(g_ev[0], st));
-    CK(launch_head(a, a.n_frames * a.n_rays, st));
+    if (m.mlp_precision == 0) CK(launch_head(a, a.n_frames * a.n_rays, st));
+    else CK(launch_head_tc(a, m.tc, m.mlp_precision, a.n_frames * a.n_rays, st));
     if (g_profile) CKN(cudaEventRecord(g_ev[1], st));
     CK(launch_schedule(a.hist, a.n_frames, a.n_rays, a.max_steps, a.B_total, st));
     a.pass = 2;
     a.cursor = counters + 1;
-    CK(launch_head(a, -1, st));
+    if (m.mlp_precision == 0) CK(launch_head(a, -1, st));
+    else CK(launch_head_tc(a, m.tc, m.mlp_precision, -1, st));
     if (g_profile) CKN(cudaEventRecord(g_ev[2], st));
     CK(launch_epilogue(t, st));
     if (g_profile) CKN(cudaEventRecord(g_ev[3], st));

@@ -44,6 +44,19 @@ struct HeadArgs {
     int pass;                       // 1 or 2
 };
 
+// tensor-core variant: pre-swizzled 16-bit weight tiles (see pack_tc_weights in capi.cu)
+constexpr int HEAD_TC_NCHUNK = 12;
+struct HeadTcArgs {
+    const unsigned char *w_hi, *w_lo;       // streamed tiles, hi and lo images with identical layout
+    int chunk_off[HEAD_TC_NCHUNK];          // byte offset of each tile
+    int chunk_bytes[HEAD_TC_NCHUNK];        // rows * 128 (SW128 tile) or rows * 32 (K16 tile)
+    int chunk_ksteps[HEAD_TC_NCHUNK];       // MMA k-steps (16 elements each) the tile holds
+    int chunk_k16[HEAD_TC_NCHUNK];          // 1: K16 (no-swizzle) tile paired with the SH operand tile
+    const unsigned char *narrow_hi, *narrow_lo;  // 4 x [16 x 64] SW128 tiles: ambient-out k-tiles 0,1, color-out k-tiles 0,1
+};
+cudaError_t launch_head_tc(const HeadArgs &a, const HeadTcArgs &t, int precision, int total_hint, cudaStream_t st);
+size_t head_tc_smem_bytes();
+
 size_t head_smem_bytes();
 cudaError_t launch_head(const HeadArgs &a, int total_hint, cudaStream_t st);
 cudaError_t launch_schedule(const int *hist, int n_frames, int n_rays, int max_steps, int *B_total, cudaStream_t st);

@@ -27,6 +27,9 @@ from . import _capi
 from .config import GridLayout, cascade_count
 
 
+MLP_PRECISIONS = {"fp32": 0, "fp16": 1, "bf16x3": 2, "bf16": 3}
+
+
 # ------------------------------------------------------------------------------------------------ small modules
 class _MLPWeights(nn.Module):
     """Parameter container with the reference's key layout `net.{i}.weight` (cond_encoder.py:183-195, bias-free)."""
@@ -146,6 +149,9 @@ class RADNeRF(nn.Module):
                     hp["num_layers_color"] == 2 and self.cond_out_dim == 64 and self.ambient_coord_dim in (2, 3))
         if not shape_ok:
             raise NotImplementedError("libgfpp kernels are built for the May architecture (hidden 128, 3/3/2 layers, cond 64)")
+        # arithmetic of the head MLP GEMMs (gfpp_model_desc.mlp_precision): "fp32" (CUDA-core FFMA), "fp16" (tcgen05, what the
+        # reference runs under autocast), "bf16x3" (tcgen05 hi/lo split, ~fp32 accuracy), "bf16" (tcgen05)
+        self.mlp_precision = hparams.get("gfpp_mlp_precision", "fp32")
         self._packed = None  # (key, packed_dev, Model, keepalive)
         self._workspace = None
 
@@ -246,12 +252,13 @@ class RADNeRF(nn.Module):
         d.grid_size = self.grid_size
         d.density_scale = float(self.density_scale)
         d.has_torso = 0
+        d.mlp_precision = MLP_PRECISIONS[self.mlp_precision]
 
     def _ensure_packed(self):
         dev = self.density_bitfield.device
         if dev.type != "cuda":
             raise _capi.GfppError("model is not on a CUDA device: libgfpp has no CPU path (call .cuda())")
-        key = (float(self.density_scale), getattr(self, "mean_density_torso", None), dev.index)
+        key = (float(self.density_scale), getattr(self, "mean_density_torso", None), dev.index, self.mlp_precision)
         if self._packed is not None and self._packed[0] == key:
             return self._packed
         L = _capi.lib()

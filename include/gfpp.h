@@ -128,6 +128,10 @@ typedef struct {
     float density_thresh_torso;         /* min(density_thresh_torso, mean_density_torso) as the reference evaluates it */
     float torso_shrink;
     uint32_t torso_code_dim;            /* 8 */
+    /* arithmetic of the head MLP GEMMs: 0 = fp32 FFMA (CUDA cores), 1 = fp16 operands on tcgen05 tensor cores with
+     * fp32 accumulation (what the reference runs under autocast), 2 = bf16 hi/lo split x3 on tcgen05 (~fp32 accuracy),
+     * 3 = bf16 x1.  Everything else (marching, gather, compositing, torso) is fp32 in every mode. */
+    uint32_t mlp_precision;
 } gfpp_model_desc;
 
 /* Host-side model handle: plain data, caller-allocated (stack, heap, numpy buffer ...), filled by
@@ -185,6 +189,11 @@ GFPP_API int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fram
  * most recent call in milliseconds: ms[0] = head pass 1, ms[1] = schedule + head pass 2, ms[2] = torso/composite epilogue. */
 GFPP_API int gfpp_profile_enable(int on);
 GFPP_API int gfpp_profile_read(float ms[3]);
+/* Self-test of the tcgen05 plumbing (tile layouts, descriptors, MMA issue, TMEM read-back) used by the tensor-core MLP:
+ * out[128,N] = A[128,K] @ W[N,K]^T with 16-bit operands, fp32 accumulation.  K = 64*j (+16 if k16_tail), N % 16 == 0,
+ * N <= 144, K <= 144.  precision: 1 = fp16, 2 = bf16 hi/lo split (3 MMAs), 3 = bf16.  scratch: >= 6*18432 bytes. */
+GFPP_API int gfpp_tc_selftest(const float *A, const float *W, uint32_t N, uint32_t K, int k16_tail, int precision,
+                              void *scratch, float *out, void *stream);
 /* number of kernels the last gfpp_render_frames call on this thread launched */
 GFPP_API int gfpp_last_launch_count(void);
 

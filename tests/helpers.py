@@ -18,9 +18,10 @@ def lively_state(state, gain=4.0):
     return out
 
 
-def build_model(sc: scn.Scene, state=None, device="cuda"):
+def build_model(sc: scn.Scene, state=None, device="cuda", precision="fp32"):
     cls = RADNeRFTorso if sc.torso else RADNeRF
     m = cls(sc.hparams)
+    m.mlp_precision = precision
     m.load_state_dict(state if state is not None else sc.state, strict=True)
     m.density_scale = sc.density_scale
     return m.to(device).eval()
