@@ -22,6 +22,7 @@ cudaError_t launch_grid_encode(const GridMeta &, const float *, const float *, f
 cudaError_t launch_sh_encode(const float *, float *, uint32_t, uint32_t, cudaStream_t);
 cudaError_t launch_freq_encode(const float *, uint32_t, uint32_t, uint32_t, float *, cudaStream_t);
 cudaError_t launch_occupancy_bounds(const uint8_t *, uint32_t, uint32_t, int *, cudaStream_t);
+cudaError_t launch_coarse_occupancy(const uint8_t *, uint32_t, uint32_t, uint32_t *, cudaStream_t);
 // tc_pack.cu
 cudaError_t launch_pack_tc_tile(const float *, int, int, int, int, int, int, int, int, unsigned char *, unsigned char *, cudaStream_t);
 cudaError_t launch_tc_selftest(const float *, int, const unsigned char *, const unsigned char *, int, int, int, int, float *, cudaStream_t);
@@ -72,6 +73,7 @@ int fill_grid_meta(GridMeta &gm, const int32_t *offsets, uint32_t D, uint32_t L,
         gm.scale[l] = scale;
         gm.offset[l] = (uint32_t)offsets[l];
         gm.hsize[l] = hs;
+        gm.hmask[l] = (hs & (hs - 1)) == 0 ? hs - 1 : 0;
         uint32_t stride = 1;
         uint32_t mul[3] = {0, 0, 0};
         for (uint32_t d = 0; d < D && stride <= hs; ++d) {
@@ -102,6 +104,8 @@ struct ModelHost {
     const float *wide, *narrow;
     const float *wd0, *wd1, *wd2, *wc0, *wc1, *wc2;
     const int *occ_bounds;
+    const uint32_t *coarse_bits;
+    int coarse_words;
     int chunk_off[HEAD_NCHUNK];
     float aabb[6];
     float bound, min_near, density_scale, density_thresh_torso, torso_shrink;
@@ -114,7 +118,7 @@ static_assert(sizeof(ModelHost) <= sizeof(gfpp_model), "gfpp_model opaque storag
 constexpr uint32_t kMagic = 0x67667070u;  // "gfpp"
 
 struct PackedLayout {
-    size_t wide, narrow, wd0, wd1, wd2, wc0, wc1, wc2, occ, tc_hi, tc_lo, tcn_hi, tcn_lo, total;
+    size_t wide, narrow, wd0, wd1, wd2, wc0, wc1, wc2, occ, coarse, tc_hi, tc_lo, tcn_hi, tcn_lo, total;
 };
 
 // tensor-core weight stream: 12 tiles per batch (see head_tc_kernel.cu)
@@ -129,7 +133,12 @@ constexpr TcChunk kTc[HEAD_TC_NCHUNK] = {
     {5, 128, 0, 16, 1}};                         // color L0, SH columns 0..15 (K16 tile)
 inline int tc_chunk_bytes(int c) { return kTc[c].rows * (kTc[c].k16 ? 32 : 128); }
 
-PackedLayout packed_layout() {
+inline size_t coarse_words_for(uint32_t cascade, uint32_t grid_size) {
+    const size_t hc = grid_size / 4;
+    return (cascade * hc * hc * hc + 31) / 32;
+}
+
+PackedLayout packed_layout(uint32_t cascade = 8, uint32_t grid_size = 128) {
     PackedLayout L;
     size_t o = 0;
     auto take = [&](size_t floats) { size_t r = o; o += (floats * 4 + 255) / 256 * 256; return r; };
@@ -144,6 +153,7 @@ PackedLayout packed_layout() {
     L.wc1 = take(32 * 32);
     L.wc2 = take(4 * 32);
     L.occ = take(8);
+    L.coarse = take(coarse_words_for(cascade, grid_size));
     size_t tcb = 0;
     for (int c = 0; c < HEAD_TC_NCHUNK; ++c) tcb += (size_t)tc_chunk_bytes(c);
     L.tc_hi = take(tcb / 4);
@@ -324,13 +334,15 @@ int gfpp_tc_selftest(const float *A, const float *W, uint32_t N, uint32_t K, int
 
 // ------------------------------------------------------------------ (B) fused renderer
 size_t gfpp_model_packed_bytes(const gfpp_model_desc *desc) {
-    (void)desc;
-    return packed_layout().total;
+    if (!desc) return packed_layout().total;
+    return packed_layout(desc->cascade, desc->grid_size).total;
 }
 
 int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes, gfpp_model *model, void *stream) {
     if (!d || !packed || !model) return fail(GFPP_ERR_INVALID, "model_pack: null pointer%s");
-    const PackedLayout L = packed_layout();
+    if (d->cascade < 1 || d->cascade > 8 || d->grid_size < 8 || d->grid_size > 1024 || d->grid_size % 4)
+        return fail(GFPP_ERR_UNSUPPORTED, "model_pack: cascade/grid_size out of range%s");
+    const PackedLayout L = packed_layout(d->cascade, d->grid_size);
     if (packed_bytes < L.total) return fail(GFPP_ERR_WORKSPACE, "model_pack: packed buffer too small%s");
     if (d->cond_dim != 64 || d->ind_dim > 16) return fail(GFPP_ERR_UNSUPPORTED, "model_pack: cond_dim must be 64, ind_dim <= 16%s");
     if (d->cascade < 1 || d->cascade > 8 || d->grid_size < 8 || d->grid_size > 1024)
@@ -401,6 +413,12 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
     const uint32_t H3 = d->grid_size * d->grid_size * d->grid_size;
     CK(launch_occupancy_bounds(d->density_bitfield, d->cascade * H3 / 8, H3, occ, st));
     m.occ_bounds = occ;
+    // coarse (4x4x4 OR-pooled) occupancy: lets the marcher skip empty space without touching the fine bitfield
+    uint32_t *coarse = (uint32_t *)(base + L.coarse);
+    m.coarse_words = (int)coarse_words_for(d->cascade, d->grid_size);
+    CKN(cudaMemsetAsync(coarse, 0, (size_t)m.coarse_words * 4, st));
+    CK(launch_coarse_occupancy(d->density_bitfield, d->cascade, d->grid_size, coarse, st));
+    m.coarse_bits = coarse;
 
     m.mlp_precision = (int)d->mlp_precision;
     if (d->mlp_precision > 3) return fail(GFPP_ERR_UNSUPPORTED, "model_pack: mlp_precision must be 0..3%s");
@@ -496,6 +514,8 @@ int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfp
     for (int c = 0; c < HEAD_NCHUNK; ++c) { a.chunk_off[c] = m.chunk_off[c]; a.chunk_k[c] = kChunkK[c]; }
     march_const_init(a.mc, m.bound, fr->dt_gamma, fr->max_steps, m.cascade, m.grid_size, m.bitfield);
     a.occ_bounds = m.occ_bounds;
+    a.coarse_bits = m.coarse_bits;
+    a.coarse_words = m.coarse_words;
     memcpy(a.aabb, m.aabb, sizeof(a.aabb));
     a.min_near = m.min_near; a.density_scale = m.density_scale;
     a.use_occ_box = m.use_occ_box;

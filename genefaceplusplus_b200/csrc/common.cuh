@@ -36,6 +36,10 @@ struct MarchConst {
     // tight cell-space bounds of the occupied voxels of cascade 0..C-1 (inclusive); cells outside are
     // known empty, so their bit need not be read.  lo > hi means "no bounds available: always read".
     int bb_lo[3], bb_hi[3];
+    // optional coarse occupancy: bit (level*Hc^3 + (cx*Hc + cy)*Hc + cz) is the OR of the 4x4x4 fine cells of coarse
+    // cell (cx,cy,cz); a clear bit proves the fine cell empty without touching the fine bitfield (nullptr: unused).
+    const uint32_t *coarse;
+    uint32_t Hc;
 };
 
 __host__ __device__ inline void march_const_init(MarchConst &mc, float bound, float dt_gamma, uint32_t max_steps,
@@ -56,6 +60,8 @@ __host__ __device__ inline void march_const_init(MarchConst &mc, float bound, fl
     mc.bits = bits;
     mc.bb_lo[0] = mc.bb_lo[1] = mc.bb_lo[2] = 1;
     mc.bb_hi[0] = mc.bb_hi[1] = mc.bb_hi[2] = 0;
+    mc.coarse = nullptr;
+    mc.Hc = H / 4;
 }
 
 struct RayGeom {
@@ -94,11 +100,15 @@ __device__ __forceinline__ float step_len(const MarchConst &mc, float t) {
 }
 
 // cell coordinate along one axis: (int)clamp(0.5 * (p * rb + 1) * H, 0, H-1) with the product taken in
-// DOUBLE because of the reference's 0.5 literal (raymarching.cu:890-892)
+// DOUBLE because of the reference's 0.5 literal (raymarching.cu:890-892).  When H is a power of two the double
+// product 0.5*u*H is exactly the float product u*(H/2) (scaling by a power of two is exact), so the fp64 pipe is
+// only used for odd grid sizes.
 __device__ __forceinline__ int cell_of(float p, float mip_rbound, const MarchConst &mc) {
     const float u = __fadd_rn(__fmul_rn(p, mip_rbound), 1.0f);
-    const double v = __dmul_rn(__dmul_rn(0.5, (double)u), (double)mc.H);
-    return (int)clampf(__double2float_rn(v), 0.0f, mc.Hm1);
+    float c;
+    if ((mc.H & (mc.H - 1)) == 0) c = __fmul_rn(u, 0.5f * mc.fH);
+    else c = __double2float_rn(__dmul_rn(__dmul_rn(0.5, (double)u), (double)mc.H));
+    return (int)clampf(c, 0.0f, mc.Hm1);
 }
 
 // Advance `t` to the next occupied sample on the ray.  On success returns true with the sample
@@ -106,14 +116,19 @@ __device__ __forceinline__ int cell_of(float p, float mip_rbound, const MarchCon
 // "occupied" iteration of the reference loop.  Returns false when t >= far (ray exhausted).
 __device__ __forceinline__ bool march_next(const MarchConst &mc, const RayGeom &g, float far, float &t, float &x,
                                            float &y, float &z, float &dt) {
+    // with a single cascade the mip level is always 0 (raymarching.cu:881-886): hoist its constants out of the loop
+    const bool single = mc.C == 1;
+    int level = 0;
+    float mip_bound = fminf(1.0f, mc.bound);
+    float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+    const float sx = copysignf(1.0f, g.dx), sy = copysignf(1.0f, g.dy), sz = copysignf(1.0f, g.dz);
+    const bool have_bb = mc.bb_lo[0] <= mc.bb_hi[0];
     while (t < far) {
         x = clampf(__fadd_rn(g.ox, __fmul_rn(t, g.dx)), -mc.bound, mc.bound);
         y = clampf(__fadd_rn(g.oy, __fmul_rn(t, g.dy)), -mc.bound, mc.bound);
         z = clampf(__fadd_rn(g.oz, __fmul_rn(t, g.dz)), -mc.bound, mc.bound);
         dt = step_len(mc, t);
-        int level = 0;
-        float mip_bound = fminf(1.0f, mc.bound), mip_rbound;
-        if (mc.C > 1) {
+        if (!single) {
             int e1, e2;
             (void)frexpf(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), &e1);
             // mip_from_dt: dt * H in float, then * 0.5 in double, rounded to float (raymarching.cu:50)
@@ -122,13 +137,16 @@ __device__ __forceinline__ bool march_next(const MarchConst &mc, const RayGeom &
             const int l2 = (int)fminf(mc.fC - 1.0f, fmaxf(0.0f, (float)e2));
             level = max(l1, l2);
             mip_bound = fminf(scalbnf(1.0f, level), mc.bound);
+            mip_rbound = __fdiv_rn(1.0f, mip_bound);
         }
-        mip_rbound = __fdiv_rn(1.0f, mip_bound);
         const int nx = cell_of(x, mip_rbound, mc), ny = cell_of(y, mip_rbound, mc), nz = cell_of(z, mip_rbound, mc);
         bool occ = false;
-        const bool known_empty = (mc.bb_lo[0] <= mc.bb_hi[0]) &&
-                                 (nx < mc.bb_lo[0] || nx > mc.bb_hi[0] || ny < mc.bb_lo[1] || ny > mc.bb_hi[1] ||
-                                  nz < mc.bb_lo[2] || nz > mc.bb_hi[2]);
+        bool known_empty = have_bb && (nx < mc.bb_lo[0] || nx > mc.bb_hi[0] || ny < mc.bb_lo[1] || ny > mc.bb_hi[1] ||
+                                       nz < mc.bb_lo[2] || nz > mc.bb_hi[2]);
+        if (!known_empty && mc.coarse) {
+            const uint32_t ci = (uint32_t)level * mc.Hc * mc.Hc * mc.Hc + (((uint32_t)nx >> 2) * mc.Hc + ((uint32_t)ny >> 2)) * mc.Hc + ((uint32_t)nz >> 2);
+            known_empty = ((mc.coarse[ci >> 5] >> (ci & 31)) & 1u) == 0u;
+        }
         if (!known_empty) {
             // bit index formed in float (raymarching.cu:894): exact while below 2^24
             const uint32_t bit = (uint32_t)__fadd_rn(__fmul_rn((float)level, mc.H3),
@@ -140,7 +158,6 @@ __device__ __forceinline__ bool march_next(const MarchConst &mc, const RayGeom &
             return true;
         }
         // distance to the far face of this voxel along the ray (raymarching.cu:916-919)
-        const float sx = copysignf(1.0f, g.dx), sy = copysignf(1.0f, g.dy), sz = copysignf(1.0f, g.dz);
         const float fx = __fadd_rn(__fadd_rn((float)nx, 0.5f), __fmul_rn(0.5f, sx));
         const float fy = __fadd_rn(__fadd_rn((float)ny, 0.5f), __fmul_rn(0.5f, sy));
         const float fz = __fadd_rn(__fadd_rn((float)nz, 0.5f), __fmul_rn(0.5f, sz));
@@ -165,10 +182,12 @@ struct GridMeta {
     uint32_t mul1[GFPP_MAX_LEVELS];    // stride of dim 1 (0 if the dim is dropped: get_grid_index quirk, H5)
     uint32_t mul2[GFPP_MAX_LEVELS];    // stride of dim 2 (0 if dropped)
     uint32_t hashed[GFPP_MAX_LEVELS];  // 1 if gridtype==hash and the level overflows its table
+    uint32_t hmask[GFPP_MAX_LEVELS];   // hsize-1 when hsize is a power of two (index % hsize == index & hmask), else 0
     uint32_t num_levels, dim, interp;
     float align_off;                   // 0.5 unless align_corners
 };
 
+// table slot of integer cell (x,y,z) in level l: get_grid_index (gridencoder.cu:66-84)
 __device__ __forceinline__ uint32_t grid_slot(const GridMeta &gm, int l, uint32_t x, uint32_t y, uint32_t z) {
     uint32_t idx;
     if (gm.hashed[l]) {
@@ -176,6 +195,10 @@ __device__ __forceinline__ uint32_t grid_slot(const GridMeta &gm, int l, uint32_
     } else {
         idx = x + y * gm.mul1[l] + z * gm.mul2[l];
     }
+    // index % hashmap_size (gridencoder.cu:83).  Capped levels have a power-of-two size (2^log2_hashmap_size): one AND;
+    // uncapped levels hold the whole dense grid, so the generic modulo is almost never taken.
+    const uint32_t hm = gm.hmask[l];
+    if (hm) return idx & hm;
     const uint32_t hs = gm.hsize[l];
     if (idx >= hs) idx %= hs;
     return idx;
@@ -198,16 +221,28 @@ __device__ __forceinline__ float2 grid_lookup3(const GridMeta &gm, const float2 
     }
     const float2 *tb = table + gm.offset[l];
     float2 c[8];
+    if (!gm.hashed[l]) {
+        // tiled level: the 8 corner slots differ by fixed strides -- one base index, adds, and a mask (or the rare modulo)
+        const uint32_t m1 = gm.mul1[l], m2 = gm.mul2[l], hm = gm.hmask[l], hs = gm.hsize[l];
+        const uint32_t base = gx + gy * m1 + gz * m2;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-        c[i] = __ldg(tb + grid_slot(gm, l, gx + (i & 1), gy + ((i >> 1) & 1), gz + ((i >> 2) & 1)));
+        for (int i = 0; i < 8; ++i) {
+            uint32_t idx = base + (i & 1) + ((i & 2) ? m1 : 0u) + ((i & 4) ? m2 : 0u);
+            if (hm) idx &= hm;
+            else if (idx >= hs) idx %= hs;
+            c[i] = __ldg(tb + idx);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            c[i] = __ldg(tb + grid_slot(gm, l, gx + (i & 1), gy + ((i >> 1) & 1), gz + ((i >> 2) & 1)));
+    }
+    // same factor order as the reference: w = 1; w *= (x term); w *= (y term); w *= (z term)
+    const float wx[2] = {1.0f - px, px}, wy[2] = {1.0f - py, py}, wz[2] = {1.0f - pz, pz};
     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        // same factor order as the reference: w = 1; w *= (x term); w *= (y term); w *= (z term)
-        float wgt = (i & 1) ? px : 1.0f - px;
-        wgt *= (i & 2) ? py : 1.0f - py;
-        wgt *= (i & 4) ? pz : 1.0f - pz;
+        const float wgt = wx[i & 1] * wy[(i >> 1) & 1] * wz[(i >> 2) & 1];
         acc.x += wgt * c[i].x;
         acc.y += wgt * c[i].y;
     }

@@ -78,5 +78,173 @@ __device__ __forceinline__ void finalize_ray(const HeadArgs &a, const Slot &s, b
 }
 
 
+
+// padded world-space box of the occupied voxels (cascade 0) from the device-side cell bounds; also installs the cell
+// bounds into `mc`.  Rays whose [near, far] segment misses the box have no sample.
+__device__ __forceinline__ bool setup_occupancy(const HeadArgs &a, MarchConst &mc, float (&occ_lo)[3], float (&occ_hi)[3]) {
+    bool have_box = false;
+    if (a.occ_bounds) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { mc.bb_lo[k] = a.occ_bounds[k]; mc.bb_hi[k] = a.occ_bounds[3 + k]; }
+        if (a.use_occ_box) {
+            have_box = true;
+            const float mb = fminf(1.0f, mc.bound);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (mc.bb_hi[k] < mc.bb_lo[k]) { occ_lo[k] = 1e30f; occ_hi[k] = -1e30f; }  // nothing occupied
+                else {
+                    occ_lo[k] = ((float)(mc.bb_lo[k] - 1) * mc.rH * 2.0f - 1.0f) * mb;
+                    occ_hi[k] = ((float)(mc.bb_hi[k] + 2) * mc.rH * 2.0f - 1.0f) * mb;
+                }
+            }
+        }
+    }
+    return have_box;
+}
+
+// one out-of-line copy of the marcher per kernel (three call sites; the kernels must stay I-cache friendly)
+// (results by value: reference parameters would force the marcher's loop state through local memory)
+struct MarchOut {
+    float t, x, y, z, dt;
+    int ok;
+};
+static __device__ __noinline__ MarchOut march_next_out(const MarchConst &mc, const RayGeom &g, float far, float t0) {
+    float t = t0, x = 0.f, y = 0.f, z = 0.f, dt = 0.f;
+    const bool ok = march_next(mc, g, far, t, x, y, z, dt);
+    MarchOut o;
+    o.t = t; o.x = x; o.y = y; o.z = z; o.dt = dt; o.ok = ok ? 1 : 0;
+    return o;
+}
+__device__ __forceinline__ bool march_next_nl(const MarchConst &mc, const RayGeom &g, float far, float &t, float &x, float &y, float &z,
+                                              float &dt) {
+#ifdef GFPP_OUTLINE_MARCH
+    const MarchOut o = march_next_out(mc, g, far, t);
+    t = o.t; x = o.x; y = o.y; z = o.z; dt = o.dt;
+    return o.ok != 0;
+#else
+    return march_next(mc, g, far, t, x, y, z, dt);
+#endif
+}
+
+constexpr int kFetchTries = 4;   // rays a thread may try per refill iteration (most candidates are cheap misses)
+constexpr int kRefillIters = 2;
+
+// Refill dead slots from the global work cursor, then publish the batch (valid flags, frame ids, sample positions).
+// Returns the number of valid rows, or -1 when the CTA is out of work.  All threads of the CTA must call it.
+template <class SmemT>
+__device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, Slot &sl, const MarchConst &mc, bool have_box,
+                                                  const float (&occ_lo)[3], const float (&occ_hi)[3], int total, int tid) {
+    constexpr int TM = HEAD_TM;
+    for (int it = 0; it < kRefillIters; ++it) {
+        if (tid == 0 && s.next >= s.end && !s.done) {
+            const int base = atomicAdd(a.cursor, TM);
+            if (base >= total) { s.done = 1; }
+            else { s.next = base; s.end = min(base + TM, total); }
+        }
+        __syncthreads();
+        if (tid < TM && !sl.active) {
+            for (int attempt = 0; attempt < kFetchTries && !sl.active && s.next < s.end; ++attempt) {
+                const int w = atomicAdd(&s.next, 1);
+                if (w >= s.end) break;
+                int gid = w;
+                if (a.pass == 2) gid = a.survivors[w];
+                sl.gid = gid;
+                sl.frame = gid / a.n_rays;
+                const int ray = gid - sl.frame * a.n_rays;
+                load_ray(a, sl.frame, ray, sl.g);
+                near_far(sl.g, a.aabb, a.min_near, sl.near, sl.far);
+                bool live;
+                if (a.pass == 1) {
+                    sl.t = sl.near; sl.ws = 0.f; sl.depth = 0.f; sl.r = sl.gch = sl.b = 0.f;
+                    sl.nsamp = 0; sl.cap = a.max_steps;
+                    live = may_hit_occupied(have_box, occ_lo, occ_hi, sl.g, sl.near, sl.far) &&
+                           march_next_nl(mc, sl.g, sl.far, sl.t, sl.px, sl.py, sl.pz, sl.dt);
+                    if (!live) {  // no sample at all: the ray dies at position 1 (delta == 0)
+                        finalize_ray(a, sl, true);
+                        warp_agg_add(a.hist, sl.frame * (a.max_steps + 2) + 1, 1);
+                    }
+                } else {
+                    const size_t g = (size_t)gid;
+                    sl.t = a.rays_t[g]; sl.ws = a.wsum[g]; sl.depth = a.depth[g];
+                    sl.r = a.image[3 * g]; sl.gch = a.image[3 * g + 1]; sl.b = a.image[3 * g + 2];
+                    sl.nsamp = a.max_steps; sl.cap = a.B_total[sl.frame];
+                    live = sl.nsamp < sl.cap && march_next_nl(mc, sl.g, sl.far, sl.t, sl.px, sl.py, sl.pz, sl.dt);
+                    if (!live) finalize_ray(a, sl, true);
+                }
+                sl.active = live;
+            }
+        }
+        // another iteration only pays off when slots are still empty AND the local chunk ran dry while work remains
+        const int want_more = __syncthreads_or(tid < TM && !sl.active && s.next >= s.end && !s.done);
+        if (!want_more) break;
+    }
+    if (tid < TM) {
+        s.valid[tid] = sl.active ? 1 : 0;
+        s.frame[tid] = sl.frame;
+        s.sx[tid] = sl.px; s.sy[tid] = sl.py; s.sz[tid] = sl.pz;
+    }
+    const int n_valid = __syncthreads_count(tid < TM && sl.active);
+    if (n_valid == 0) {
+        const bool out_of_work = s.done && s.next >= s.end;
+        __syncthreads();  // thread 0 must not start the next refill (which rewrites next/end/done) before everyone has read them
+        return out_of_work ? -1 : 0;
+    }
+    return n_valid;
+}
+
+// Front-to-back compositing of the batch's sample in the owner thread (raymarching.cu:978-1006), termination test,
+// then march to the ray's next sample (or retire the ray).
+template <class SmemT>
+__device__ __forceinline__ void composite_and_advance(const HeadArgs &a, SmemT &s, Slot &sl, const MarchConst &mc, int tid) {
+    constexpr int TM = HEAD_TM;
+    if (tid < TM && sl.active) {
+        const float sigma = s.sig[tid];
+        const float alpha = 1.0f - expf(-sigma * sl.dt);
+        const float T = 1.0f - sl.ws;
+        const float w = alpha * T;
+        sl.ws += w;
+        sl.depth += w * sl.t;  // sl.t is already the post-sample t (deltas[1])
+        sl.r += w * s.rgb[tid];
+        sl.gch += w * s.rgb[TM + tid];
+        sl.b += w * s.rgb[2 * TM + tid];
+        sl.nsamp += 1;
+        if (a.valid_samples) warp_agg_add(a.valid_samples, sl.frame, 1);
+        int D = 0;  // death index (1-based sample position), 0 = still alive
+        bool suspend = false;
+        if (T < a.T_thresh) D = sl.nsamp;
+        else if (sl.nsamp >= sl.cap) suspend = true;
+        else if (!march_next_nl(mc, sl.g, sl.far, sl.t, sl.px, sl.py, sl.pz, sl.dt)) D = sl.nsamp + 1;
+        if (D) {
+            finalize_ray(a, sl, true);
+            if (a.pass == 1) warp_agg_add(a.hist, sl.frame * (a.max_steps + 2) + D, 1);
+            sl.active = false;
+        } else if (suspend) {
+            if (a.pass == 1) {
+                finalize_ray(a, sl, false);  // raw depth: pass 2 keeps accumulating
+                a.rays_t[sl.gid] = sl.t;
+                cg::coalesced_group grp = cg::coalesced_threads();
+                int base = 0;
+                if (grp.thread_rank() == 0) base = atomicAdd(a.n_survivors, (int)grp.size());
+                base = grp.shfl(base, 0);
+                a.survivors[base + grp.thread_rank()] = sl.gid;
+            } else {
+                finalize_ray(a, sl, true);
+            }
+            sl.active = false;
+        }
+    }
+}
+
+// copy the coarse occupancy words into shared memory and point the marcher at them
+template <class SmemT>
+__device__ __forceinline__ void install_coarse(const HeadArgs &a, SmemT &s, MarchConst &mc, int tid, int nthreads) {
+    if (a.coarse_bits && a.coarse_words <= HEAD_COARSE_WORDS) {
+        for (int i = tid; i < a.coarse_words; i += nthreads) s.coarse[i] = a.coarse_bits[i];
+        mc.coarse = s.coarse;
+    } else {
+        mc.coarse = a.coarse_bits;   // too large for the smem slot (cascade > 2): read through L1/L2
+    }
+}
+
 }  // namespace headc
 }  // namespace gfpp

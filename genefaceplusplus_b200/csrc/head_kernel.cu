@@ -39,7 +39,6 @@ constexpr int LDA = 148;                  // A-tile row stride in floats (16B al
 constexpr int LDP = 36;                   // position-feature copy stride
 constexpr int WCHUNK = 72 * 128;          // floats per weight stage (largest chunk: 72 k-rows)
 constexpr int NSTAGE = 2;
-constexpr int REFILL_ITERS = 3;
 
 struct Smem {
     float A[TM * LDA];
@@ -53,6 +52,7 @@ struct Smem {
     int frame[TM];
     int valid[TM];
     unsigned long long bar[NSTAGE];
+    uint32_t coarse[HEAD_COARSE_WORDS];
     int next, end, done;
 };
 
@@ -206,26 +206,9 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ Hea
 
     // ---- one-time setup ----
     MarchConst mc = a.mc;
-    // padded world-space box of the occupied voxels: rays whose [near, far] segment misses it have no sample.
-    // Only valid for a single cascade whose aabb lies inside the cube (host sets use_occ_box accordingly).
     float occ_lo[3] = {0.f, 0.f, 0.f}, occ_hi[3] = {0.f, 0.f, 0.f};
-    bool have_box = false;
-    if (a.occ_bounds) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { mc.bb_lo[k] = a.occ_bounds[k]; mc.bb_hi[k] = a.occ_bounds[3 + k]; }
-        if (a.use_occ_box) {
-            have_box = true;
-            const float mb = fminf(1.0f, mc.bound);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (mc.bb_hi[k] < mc.bb_lo[k]) { occ_lo[k] = 1e30f; occ_hi[k] = -1e30f; }  // nothing occupied
-                else {
-                    occ_lo[k] = ((float)(mc.bb_lo[k] - 1) * mc.rH * 2.0f - 1.0f) * mb;
-                    occ_hi[k] = ((float)(mc.bb_hi[k] + 2) * mc.rH * 2.0f - 1.0f) * mb;
-                }
-            }
-        }
-    }
+    const bool have_box = setup_occupancy(a, mc, occ_lo, occ_hi);
+    install_coarse(a, s, mc, tid, NT);
     for (int i = tid; i < 8 * 128; i += NT) s.narrow[i] = a.narrow[i];
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) mbar_init(&s.bar[i], 1);
@@ -244,61 +227,10 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ Hea
     sl.gid = 0; sl.frame = 0; sl.nsamp = 0; sl.cap = 0;
 
     for (;;) {
-        // ================= refill dead slots from the global cursor =================
-        for (int it = 0; it < REFILL_ITERS; ++it) {
-            if (tid == 0 && s.next >= s.end && !s.done) {
-                const int base = atomicAdd(a.cursor, TM);
-                if (base >= total) { s.done = 1; }
-                else { s.next = base; s.end = min(base + TM, total); }
-            }
-            __syncthreads();
-            if (tid < TM && !sl.active && s.next < s.end) {
-                const int w = atomicAdd(&s.next, 1);
-                if (w < s.end) {
-                    int gid = w;
-                    if (a.pass == 2) gid = a.survivors[w];
-                    sl.gid = gid;
-                    sl.frame = gid / a.n_rays;
-                    const int ray = gid - sl.frame * a.n_rays;
-                    load_ray(a, sl.frame, ray, sl.g);
-                    near_far(sl.g, a.aabb, a.min_near, sl.near, sl.far);
-                    bool live;
-                    if (a.pass == 1) {
-                        sl.t = sl.near; sl.ws = 0.f; sl.depth = 0.f; sl.r = sl.gch = sl.b = 0.f;
-                        sl.nsamp = 0; sl.cap = a.max_steps;
-                        live = may_hit_occupied(have_box, occ_lo, occ_hi, sl.g, sl.near, sl.far) &&
-                               march_next(mc, sl.g, sl.far, sl.t, sl.px, sl.py, sl.pz, sl.dt);
-                        if (!live) {  // no sample at all: the ray dies at position 1 (delta == 0)
-                            finalize_ray(a, sl, true);
-                            warp_agg_add(a.hist, sl.frame * (a.max_steps + 2) + 1, 1);
-                        }
-                    } else {
-                        const size_t g = (size_t)gid;
-                        sl.t = a.rays_t[g]; sl.ws = a.wsum[g]; sl.depth = a.depth[g];
-                        sl.r = a.image[3 * g]; sl.gch = a.image[3 * g + 1]; sl.b = a.image[3 * g + 2];
-                        sl.nsamp = a.max_steps; sl.cap = a.B_total[sl.frame];
-                        live = sl.nsamp < sl.cap && march_next(mc, sl.g, sl.far, sl.t, sl.px, sl.py, sl.pz, sl.dt);
-                        if (!live) finalize_ray(a, sl, true);
-                    }
-                    sl.active = live;
-                }
-            }
-            __syncthreads();
-        }
-
-        // ================= publish the batch =================
-        if (tid < TM) {
-            s.valid[tid] = sl.active ? 1 : 0;
-            s.frame[tid] = sl.frame;
-            s.sx[tid] = sl.px; s.sy[tid] = sl.py; s.sz[tid] = sl.pz;
-        }
-        const int n_valid = __syncthreads_count(tid < TM && sl.active);
-        if (n_valid == 0) {
-            const bool out_of_work = s.done && s.next >= s.end;
-            __syncthreads();  // thread 0 must not start the next refill (which rewrites next/end/done) before everyone has read them
-            if (out_of_work) break;
-            continue;
-        }
+        // ================= refill dead slots from the global cursor, publish the batch (head_common.cuh) =================
+        const int n_valid = refill_and_publish(a, s, sl, mc, have_box, occ_lo, occ_hi, total, tid);
+        if (n_valid < 0) break;
+        if (n_valid == 0) continue;
 
         const int slot = tid & (TM - 1), lg = tid >> 7;
         const bool v = s.valid[slot] != 0;
@@ -430,44 +362,9 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ Hea
         }
         __syncthreads();
 
-        // ================= composite (raymarching.cu:978-1006) + advance =================
-        if (tid < TM && sl.active) {
-            const float sigma = s.sig[tid];
-            const float alpha = 1.0f - expf(-sigma * sl.dt);
-            const float T = 1.0f - sl.ws;
-            const float w = alpha * T;
-            sl.ws += w;
-            sl.depth += w * sl.t;  // sl.t is already the post-sample t (deltas[1])
-            sl.r += w * s.rgb[tid];
-            sl.gch += w * s.rgb[TM + tid];
-            sl.b += w * s.rgb[2 * TM + tid];
-            sl.nsamp += 1;
-            if (a.valid_samples) warp_agg_add(a.valid_samples, sl.frame, 1);
-            int D = 0;  // death index (1-based sample position), 0 = still alive
-            bool suspend = false;
-            if (T < a.T_thresh) D = sl.nsamp;
-            else if (sl.nsamp >= sl.cap) suspend = true;
-            else if (!march_next(mc, sl.g, sl.far, sl.t, sl.px, sl.py, sl.pz, sl.dt)) D = sl.nsamp + 1;
-            if (D) {
-                finalize_ray(a, sl, true);
-                if (a.pass == 1) warp_agg_add(a.hist, sl.frame * (a.max_steps + 2) + D, 1);
-                sl.active = false;
-            } else if (suspend) {
-                if (a.pass == 1) {
-                    finalize_ray(a, sl, false);  // raw depth: pass 2 keeps accumulating
-                    a.rays_t[sl.gid] = sl.t;
-                    cg::coalesced_group grp = cg::coalesced_threads();
-                    int base = 0;
-                    if (grp.thread_rank() == 0) base = atomicAdd(a.n_survivors, (int)grp.size());
-                    base = grp.shfl(base, 0);
-                    a.survivors[base + grp.thread_rank()] = sl.gid;
-                } else {
-                    finalize_ray(a, sl, true);
-                }
-                sl.active = false;
-            }
-        }
-        // no barrier needed here: the refill loop starts with one before smem is touched again
+        // ================= composite + advance (head_common.cuh) =================
+        composite_and_advance(a, s, sl, mc, tid);
+        // no barrier needed here: the refill starts with one before shared memory is touched again
     }
 
     // drain the prefetched weight chunks before the CTA (and its shared memory) goes away

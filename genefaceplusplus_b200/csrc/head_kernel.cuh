@@ -6,7 +6,8 @@ namespace gfpp {
 
 constexpr int HEAD_TM = 128;      // samples per batch == ray slots per CTA
 constexpr int HEAD_NT = 256;      // threads per CTA
-constexpr int HEAD_NCHUNK = 11;   // weight chunks streamed per batch (see pack_head_weights in capi.cu)
+constexpr int HEAD_NCHUNK = 11;
+constexpr int HEAD_COARSE_WORDS = 1024;   // shared-memory slot for the coarse occupancy: 32 Ki bits = one cascade of 32^3   // weight chunks streamed per batch (see pack_head_weights in capi.cu)
 
 struct HeadArgs {
     // ---- model ----
@@ -18,6 +19,8 @@ struct HeadArgs {
     const float *narrow;            // [8][128]: ambient out rows 0-2, sigma row, color out rows 0-2, color-L0 bias
     MarchConst mc;
     const int *occ_bounds;          // device [6] tight occupied-cell bounds (or nullptr)
+    const uint32_t *coarse_bits;    // device coarse occupancy (4x4x4 OR-pooled), cascade*(H/4)^3 bits, or nullptr
+    int coarse_words;
     float aabb[6];
     float min_near, density_scale;
     int use_occ_box;                // 1: reject rays that miss the padded box of occupied voxels (cascade==1, aabb inside cube)
@@ -55,7 +58,7 @@ struct HeadTcArgs {
     const unsigned char *narrow_hi, *narrow_lo;  // 4 x [16 x 64] SW128 tiles: ambient-out k-tiles 0,1, color-out k-tiles 0,1
 };
 cudaError_t launch_head_tc(const HeadArgs &a, const HeadTcArgs &t, int precision, int total_hint, cudaStream_t st);
-size_t head_tc_smem_bytes();
+size_t head_tc_smem_bytes(bool split);
 
 size_t head_smem_bytes();
 cudaError_t launch_head(const HeadArgs &a, int total_hint, cudaStream_t st);

@@ -169,7 +169,26 @@ __global__ void k_occupancy_bounds(const uint8_t *__restrict__ bits, uint32_t n_
     }
 }
 
+// ---- coarse occupancy: bit (c*Hc^3 + (cx*Hc + cy)*Hc + cz) = OR of the 4x4x4 fine cells (Morton-indexed bitfield) ----
+__global__ void k_coarse_occupancy(const uint8_t *__restrict__ bits, uint32_t C, uint32_t H, uint32_t *__restrict__ coarse) {
+    const uint32_t Hc = H / 4, n = C * Hc * Hc * Hc, H3 = H * H * H;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = i / (Hc * Hc * Hc), r = i - c * Hc * Hc * Hc;
+        const uint32_t cx = r / (Hc * Hc), cy = (r / Hc) % Hc, cz = r % Hc;
+        // a 4-aligned 4x4x4 block is 64 consecutive Morton codes = 8 consecutive bytes
+        const uint32_t m0 = morton3(cx * 4, cy * 4, cz * 4);
+        const uint64_t v = *reinterpret_cast<const uint64_t *>(bits + ((size_t)c * H3 + m0) / 8);
+        if (v) atomicOr(coarse + (i >> 5), 1u << (i & 31));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
+cudaError_t launch_coarse_occupancy(const uint8_t *bits, uint32_t C, uint32_t H, uint32_t *coarse, cudaStream_t st) {
+    const uint32_t Hc = H / 4;
+    k_coarse_occupancy<<<grid_for((uint64_t)C * Hc * Hc * Hc, 256), 256, 0, st>>>(bits, C, H, coarse);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_near_far(const float *rays_o, const float *rays_d, const float *aabb, uint32_t N, float min_near,
                             float *nears, float *fars, cudaStream_t st) {
     if (N == 0) return cudaSuccess;
