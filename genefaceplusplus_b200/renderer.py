@@ -172,7 +172,8 @@ class RADNeRF(nn.Module):
     # ------------------------------------------------------------------ conditioning (plumbing, PyTorch)
     def cal_cond_feat(self, cond, eye_area_percent=None):
         """radnerf.py:88-106.  cond: [smo_win, 1, C] -> [64]."""
-        with torch.autocast("cuda", enabled=False):
+        # fp32 end to end: no autocast, no TF32 convolutions (the 1e-3 parity bar is against the fp32 oracle)
+        with torch.autocast("cuda", enabled=False), torch.backends.cudnn.flags(allow_tf32=False):
             feat = self.cond_prenet(cond.float())
             if self.with_att:
                 feat = self.cond_att_net(feat)
@@ -181,7 +182,7 @@ class RADNeRF(nn.Module):
     def cal_cond_feat_clip(self, cond_seq):
         """All frames at once: cond_seq [T,1,C] -> [T,64]; windows as get_audio_features(att_mode=2)
         (modules/radnerfs/utils.py:86-102: centred, zero-padded)."""
-        with torch.autocast("cuda", enabled=False):
+        with torch.autocast("cuda", enabled=False), torch.backends.cudnn.flags(allow_tf32=False):
             T = cond_seq.shape[0]
             S = self.smo_win_size
             left = S // 2

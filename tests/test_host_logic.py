@@ -1,0 +1,124 @@
+"""Host-side logic on CPU: scene determinism, level layout, state_dict contract, round-schedule lemma, failure modes."""
+import numpy as np
+import pytest
+import torch
+
+from genefaceplusplus_b200 import scene as scn
+from genefaceplusplus_b200.config import GridLayout, may_hparams, may_intrinsics
+from genefaceplusplus_b200.renderer import RADNeRF, RADNeRFTorso
+
+
+def test_grid_layout_matches_reference_offsets():
+    # offsets probed from the reference's GridEncoder
+    pos = GridLayout(3)
+    assert pos.n_entries == 903480 and pos.offsets[:6].tolist() == [0, 4920, 18744, 51512, 117048, 182584]
+    tor = GridLayout(2)
+    assert tor.n_entries == 555520 and tor.offsets[:11].tolist() == [0, 296, 872, 1896, 3832, 7432, 14160, 26936, 50968, 96768, 162304]
+    assert abs(pos.per_level_scale - 1.381912879967776) < 1e-12
+
+
+def test_scene_is_deterministic_and_may_shaped():
+    a, b = scn.make_state(torso=True), scn.make_state(torso=True)
+    assert set(a) == set(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert a["position_embedder.embeddings"].shape == (903480, 2)
+    assert a["sigma_net.net.2.weight"].shape == (129, 128) and a["color_net.net.0.weight"].shape == (128, 148)
+    occ = (a["density_grid"] > 0.5).float().mean().item()
+    assert 0.017 < occ < 0.022        # ellipsoid ~1.93 % of the 128^3 cells
+    n_params = sum(a[k].numel() for k in a if k.endswith("net.0.weight") or ".net." in k)
+    assert a["density_bitfield"].dtype == torch.uint8 and a["density_bitfield"].numel() == 128 ** 3 // 8
+    fx, fy, cx, cy = may_intrinsics(512, 512)
+    assert abs(fx - 2320.0) < 1e-9 and cx == 256
+
+
+def test_dropin_modules_accept_the_reference_state_dict():
+    hp = may_hparams()
+    st = scn.make_state(torso=True, hparams=hp)
+    m = RADNeRFTorso(hp)
+    missing, unexpected = m.load_state_dict(st, strict=True)
+    assert not missing and not unexpected
+    h = RADNeRF(hp)
+    h.load_state_dict(scn.make_state(torso=False, hparams=hp), strict=True)
+    # same key set as the reference module (golden meta was produced with strict=True into the reference classes)
+    assert set(m.state_dict().keys()) == set(st.keys())
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without a GPU / on CPU tensors."""
+    from genefaceplusplus_b200 import _capi
+    sc = scn.Scene(H=8, W=8, T=2, torso=False)
+    m = RADNeRF(sc.hparams).eval()
+    m.load_state_dict(sc.state, strict=True)
+    fi = sc.frame_inputs(0)
+    with pytest.raises(_capi.GfppError):
+        m.render(fi["rays_o"], fi["rays_d"], fi["cond"], fi["bg_coords"], fi["poses"], **sc.hparams)
+    m.train()
+    with pytest.raises((NotImplementedError, _capi.GfppError)):
+        m.render(fi["rays_o"], fi["rays_d"], fi["cond"], fi["bg_coords"], fi["poses"], **sc.hparams)
+
+
+def test_unsupported_configs_raise_like_the_reference_would():
+    with pytest.raises(NotImplementedError):
+        RADNeRF(may_hparams(cond_type="nope"))
+    with pytest.raises(NotImplementedError):
+        RADNeRF(may_hparams(hidden_dim_sigma=64))
+    with pytest.raises(NotImplementedError):
+        RADNeRFTorso(may_hparams(torso_head_aware=True))
+
+
+def test_cond_feat_clip_equals_per_frame(oracle_ops):
+    """Batched conditioning (one launch set per clip) == the reference's per-frame windows incl. zero padding at the edges."""
+    from oracle.render import OracleModel
+    sc = scn.Scene(H=8, W=8, T=7, torso=False)
+    m = RADNeRF(sc.hparams).eval()
+    m.load_state_dict(sc.state, strict=True)
+    feat = m.cal_cond_feat_clip(sc.cond)
+    orc = OracleModel(sc.state, sc.hparams)
+    for t in range(7):
+        ref = orc.cal_cond_feat(scn.cond_window(sc.cond, t))
+        assert (feat[t] - ref).abs().max().item() < 1e-5, t
+        assert (m.cal_cond_feat(scn.cond_window(sc.cond, t)) - ref).abs().max().item() < 1e-5
+
+
+def test_round_schedule_lemma(oracle_ops):
+    """with perturb=False the multi-round image equals ONE round of n_step = B (the cap the schedule
+    produced), and B can be replayed from the histogram of death indices -- the property the fused kernel relies on."""
+    from oracle.render import OracleModel
+    for ds, ms in ((1.0, 8), (32.0, 16)):
+        sc = scn.Scene(H=40, W=40, T=2, torso=False, max_steps=ms, density_scale=ds)
+        fi = sc.frame_inputs(1)
+        orc = OracleModel(sc.state, sc.hparams); orc.density_scale = ds
+        ref = orc.render(fi["rays_o"], fi["rays_d"], fi["cond"], fi["bg_coords"], fi["poses"], bg_color=fi["bg_color"], T_thresh=0.01, **sc.hparams)
+        B = ref["stats"]["B_total"]
+        ro, rd = fi["rays_o"].view(-1, 3), fi["rays_d"].view(-1, 3)
+        N = ro.shape[0]
+        nears, fars = oracle_ops.near_far_from_aabb(ro, rd, sc.state["aabb_infer"], 0.05)
+        alive = torch.arange(N, dtype=torch.int32)
+        rays_t = nears.clone()
+        xyzs, dirs, deltas = oracle_ops.march_rays(N, B, alive, rays_t, ro, rd, 1.0, sc.state["density_bitfield"], 1, 128, nears, fars, 128, False, sc.hparams["dt_gamma"], ms)
+        sig, rgb, _ = orc.forward(xyzs, dirs, orc.cal_cond_feat(fi["cond"]), sc.state["individual_embeddings"][0])
+        ws = torch.zeros(N); dp = torch.zeros(N); img = torch.zeros(N, 3)
+        oracle_ops.composite_rays(N, B, alive, rays_t, sig * ds, rgb, deltas, ws, dp, img, 0.01)
+        one = (img + (1 - ws).unsqueeze(-1) * fi["bg_color"].view(-1, 3)).clamp(0, 1)
+        assert (one - ref["rgb_map"].view(-1, 3)).abs().max().item() < 1e-6
+        # replay the schedule from death indices D (1-based position of the break)
+        dl = deltas[: N * B].view(N, B, 2)
+        # D from a per-ray sequential pass
+        D = torch.full((N,), B + 1, dtype=torch.long)
+        wsum = torch.zeros(N)
+        s2 = (sig * ds)[: N * B].view(N, B)
+        done = torch.zeros(N, dtype=torch.bool)
+        for k in range(B):
+            ran_out = (dl[:, k, 0] == 0) & ~done
+            D[ran_out] = k + 1; done |= ran_out
+            T = 1 - wsum
+            wsum = torch.where(done, wsum, wsum + (1 - torch.exp(-s2[:, k] * dl[:, k, 0])) * T)
+            br = (T < 0.01) & ~done
+            D[br] = k + 1; done |= br
+        cum, n_alive, sched = 0, N, []
+        while cum < ms and n_alive > 0:
+            n_step = max(min(N // n_alive, 8), 1)
+            sched.append((n_alive, n_step)); cum += n_step
+            n_alive = int((D > cum).sum())
+        assert sched == ref["stats"]["schedule"], (sched, ref["stats"]["schedule"])
