@@ -357,6 +357,14 @@ ORC_API void orc_linear(const float *x, const float *W, float *y, uint32_t M, ui
     }
 }
 
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

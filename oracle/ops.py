@@ -48,6 +48,10 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n: int):
+    lib().orc_set_num_threads(ctypes.c_int(int(n)))
+
+
 def _f(t):
     assert t.dtype == torch.float32 and t.is_contiguous() and t.device.type == "cpu", (t.dtype, t.is_contiguous())
     return ctypes.cast(t.data_ptr(), c_f)
