@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" boundary of libgfpp.so (see include/gfpp.h for the contract).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cuda_runtime.h>
@@ -35,6 +36,7 @@ namespace {
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 bool g_profile = false;
+unsigned long long *g_phase = nullptr;
 cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
 int fail(int code, const char *fmt, const char *detail = "") {
@@ -165,7 +167,7 @@ PackedLayout packed_layout(uint32_t cascade = 8, uint32_t grid_size = 128) {
 }
 
 struct WorkLayout {
-    size_t image, rays_t, wsum, depth, survivors, zero_begin, hist, counters, B_total, valid, pcount, zero_end, bias_def,
+    size_t image, rays_t, wsum, depth, survivors, hits, zero_begin, hist, counters, B_total, valid, pcount, zero_end, bias_def,
         bias_can, total;
 };
 
@@ -179,6 +181,7 @@ WorkLayout work_layout(uint32_t F, uint32_t N, uint32_t max_steps) {
     W.wsum = take(FN * 4);
     W.depth = take(FN * 4);
     W.survivors = take(FN * 4);
+    W.hits = take(FN * 8);
     W.zero_begin = o;
     W.hist = take((size_t)F * (max_steps + 2) * 4);
     W.counters = take(16 * 4);
@@ -221,6 +224,11 @@ int gfpp_profile_enable(int on) {
             if (cudaEventCreate(&g_ev[i]) != cudaSuccess) return fail(GFPP_ERR_CUDA, "cudaEventCreate failed%s");
     }
     g_profile = on != 0;
+    return GFPP_OK;
+}
+
+int gfpp_profile_phases(void *dev_u64x32) {
+    g_phase = (unsigned long long *)dev_u64x32;
     return GFPP_OK;
 }
 
@@ -532,6 +540,8 @@ int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfp
     a.survivors = (int *)(ws + W.survivors);
     int *counters = (int *)(ws + W.counters);
     a.n_survivors = counters + 2;
+    a.hits = (int2 *)(ws + W.hits);
+    a.n_hits = counters + 3;
     a.B_total = (int *)(ws + W.B_total);
     a.valid_samples = (int *)(ws + W.valid);
 
@@ -556,11 +566,17 @@ int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfp
                                    (float *)(ws + W.bias_def), (float *)(ws + W.bias_can), st));
     }
 
+    {
+        const char *pb = getenv("GFPP_PARTNER_BUDGET");
+        a.partner_budget = pb ? atoi(pb) : 0;   // first-hit marching now lives in k_ray_setup; the in-kernel prefetcher is off
+    }
+    a.phase_cycles = g_phase;
     a.pass = 1;
     a.cursor = counters + 0;
+    CK(launch_ray_setup(a, st));
     if (g_profile) CKN(cudaEventRecord(g_ev[0], st));
-    if (m.mlp_precision == 0) CK(launch_head(a, a.n_frames * a.n_rays, st));
-    else CK(launch_head_tc(a, m.tc, m.mlp_precision, a.n_frames * a.n_rays, st));
+    if (m.mlp_precision == 0) CK(launch_head(a, -1, st));
+    else CK(launch_head_tc(a, m.tc, m.mlp_precision, -1, st));
     if (g_profile) CKN(cudaEventRecord(g_ev[1], st));
     CK(launch_schedule(a.hist, a.n_frames, a.n_rays, a.max_steps, a.B_total, st));
     a.pass = 2;

@@ -111,65 +111,115 @@ __device__ __forceinline__ int cell_of(float p, float mip_rbound, const MarchCon
     return (int)clampf(c, 0.0f, mc.Hm1);
 }
 
+// Loop-invariant pieces of the marcher (single cascade: the mip level is always 0, raymarching.cu:881-886).
+struct MarchHoist {
+    bool single, have_bb;
+    float mip_bound, mip_rbound, sx, sy, sz;
+};
+__device__ __forceinline__ void march_hoist(const MarchConst &mc, const RayGeom &g, MarchHoist &h) {
+    h.single = mc.C == 1;
+    h.mip_bound = fminf(1.0f, mc.bound);
+    h.mip_rbound = __fdiv_rn(1.0f, h.mip_bound);
+    h.sx = copysignf(1.0f, g.dx); h.sy = copysignf(1.0f, g.dy); h.sz = copysignf(1.0f, g.dz);
+    h.have_bb = mc.bb_lo[0] <= mc.bb_hi[0];
+}
+
+// One iteration of the reference loop (raymarching.cu:873-927) at parameter t (< far).  Occupied cell: returns true with
+// the sample (x,y,z,dt) and t UNCHANGED.  Empty cell: advances t past the voxel and returns false.  `cost` is incremented
+// by 4 when the fine bitfield had to be read and by 1 otherwise (used to bound per-round prefetch work).
+__device__ __forceinline__ bool march_cell(const MarchConst &mc, const RayGeom &g, const MarchHoist &h, float &t, float &x, float &y,
+                                           float &z, float &dt, int &cost) {
+    x = clampf(__fadd_rn(g.ox, __fmul_rn(t, g.dx)), -mc.bound, mc.bound);
+    y = clampf(__fadd_rn(g.oy, __fmul_rn(t, g.dy)), -mc.bound, mc.bound);
+    z = clampf(__fadd_rn(g.oz, __fmul_rn(t, g.dz)), -mc.bound, mc.bound);
+    dt = step_len(mc, t);
+    int level = 0;
+    float mip_bound = h.mip_bound, mip_rbound = h.mip_rbound;
+    if (!h.single) {
+        int e1, e2;
+        (void)frexpf(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), &e1);
+        // mip_from_dt: dt * H in float, then * 0.5 in double, rounded to float (raymarching.cu:50)
+        (void)frexpf(__double2float_rn(__dmul_rn((double)__fmul_rn(dt, mc.fH), 0.5)), &e2);
+        const int l1 = (int)fminf(mc.fC - 1.0f, fmaxf(0.0f, (float)e1));
+        const int l2 = (int)fminf(mc.fC - 1.0f, fmaxf(0.0f, (float)e2));
+        level = max(l1, l2);
+        mip_bound = fminf(scalbnf(1.0f, level), mc.bound);
+        mip_rbound = __fdiv_rn(1.0f, mip_bound);
+    }
+    const int nx = cell_of(x, mip_rbound, mc), ny = cell_of(y, mip_rbound, mc), nz = cell_of(z, mip_rbound, mc);
+    bool occ = false;
+    bool known_empty = h.have_bb && (nx < mc.bb_lo[0] || nx > mc.bb_hi[0] || ny < mc.bb_lo[1] || ny > mc.bb_hi[1] ||
+                                     nz < mc.bb_lo[2] || nz > mc.bb_hi[2]);
+    if (!known_empty && mc.coarse) {
+        const uint32_t ci = (uint32_t)level * mc.Hc * mc.Hc * mc.Hc + (((uint32_t)nx >> 2) * mc.Hc + ((uint32_t)ny >> 2)) * mc.Hc + ((uint32_t)nz >> 2);
+        known_empty = ((mc.coarse[ci >> 5] >> (ci & 31)) & 1u) == 0u;
+    }
+    if (!known_empty) {
+        // bit index formed in float (raymarching.cu:894): exact while below 2^24
+        const uint32_t bit = (uint32_t)__fadd_rn(__fmul_rn((float)level, mc.H3),
+                                                 (float)morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
+        occ = (__ldg(mc.bits + (bit >> 3)) >> (bit & 7)) & 1;
+        cost += 4;
+    } else {
+        cost += 1;
+    }
+    if (occ) return true;
+    // distance to the far face of this voxel along the ray (raymarching.cu:916-919)
+    const float fx = __fadd_rn(__fadd_rn((float)nx, 0.5f), __fmul_rn(0.5f, h.sx));
+    const float fy = __fadd_rn(__fadd_rn((float)ny, 0.5f), __fmul_rn(0.5f, h.sy));
+    const float fz = __fadd_rn(__fadd_rn((float)nz, 0.5f), __fmul_rn(0.5f, h.sz));
+    const float tx = __fmul_rn(__fsub_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(fx, mc.rH), 2.0f), 1.0f), mip_bound), x), g.rdx);
+    const float ty = __fmul_rn(__fsub_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(fy, mc.rH), 2.0f), 1.0f), mip_bound), y), g.rdy);
+    const float tz = __fmul_rn(__fsub_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(fz, mc.rH), 2.0f), 1.0f), mip_bound), z), g.rdz);
+    const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    do {
+        t = __fadd_rn(t, step_len(mc, t));
+    } while (t < tt);
+    return false;
+}
+
 // Advance `t` to the next occupied sample on the ray.  On success returns true with the sample
 // position (x,y,z), its step dt, and t already advanced PAST the sample (t += dt), exactly like one
 // "occupied" iteration of the reference loop.  Returns false when t >= far (ray exhausted).
 __device__ __forceinline__ bool march_next(const MarchConst &mc, const RayGeom &g, float far, float &t, float &x,
                                            float &y, float &z, float &dt) {
-    // with a single cascade the mip level is always 0 (raymarching.cu:881-886): hoist its constants out of the loop
-    const bool single = mc.C == 1;
-    int level = 0;
-    float mip_bound = fminf(1.0f, mc.bound);
-    float mip_rbound = __fdiv_rn(1.0f, mip_bound);
-    const float sx = copysignf(1.0f, g.dx), sy = copysignf(1.0f, g.dy), sz = copysignf(1.0f, g.dz);
-    const bool have_bb = mc.bb_lo[0] <= mc.bb_hi[0];
+    MarchHoist h;
+    march_hoist(mc, g, h);
+    int cost = 0;
     while (t < far) {
-        x = clampf(__fadd_rn(g.ox, __fmul_rn(t, g.dx)), -mc.bound, mc.bound);
-        y = clampf(__fadd_rn(g.oy, __fmul_rn(t, g.dy)), -mc.bound, mc.bound);
-        z = clampf(__fadd_rn(g.oz, __fmul_rn(t, g.dz)), -mc.bound, mc.bound);
-        dt = step_len(mc, t);
-        if (!single) {
-            int e1, e2;
-            (void)frexpf(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), &e1);
-            // mip_from_dt: dt * H in float, then * 0.5 in double, rounded to float (raymarching.cu:50)
-            (void)frexpf(__double2float_rn(__dmul_rn((double)__fmul_rn(dt, mc.fH), 0.5)), &e2);
-            const int l1 = (int)fminf(mc.fC - 1.0f, fmaxf(0.0f, (float)e1));
-            const int l2 = (int)fminf(mc.fC - 1.0f, fmaxf(0.0f, (float)e2));
-            level = max(l1, l2);
-            mip_bound = fminf(scalbnf(1.0f, level), mc.bound);
-            mip_rbound = __fdiv_rn(1.0f, mip_bound);
-        }
-        const int nx = cell_of(x, mip_rbound, mc), ny = cell_of(y, mip_rbound, mc), nz = cell_of(z, mip_rbound, mc);
-        bool occ = false;
-        bool known_empty = have_bb && (nx < mc.bb_lo[0] || nx > mc.bb_hi[0] || ny < mc.bb_lo[1] || ny > mc.bb_hi[1] ||
-                                       nz < mc.bb_lo[2] || nz > mc.bb_hi[2]);
-        if (!known_empty && mc.coarse) {
-            const uint32_t ci = (uint32_t)level * mc.Hc * mc.Hc * mc.Hc + (((uint32_t)nx >> 2) * mc.Hc + ((uint32_t)ny >> 2)) * mc.Hc + ((uint32_t)nz >> 2);
-            known_empty = ((mc.coarse[ci >> 5] >> (ci & 31)) & 1u) == 0u;
-        }
-        if (!known_empty) {
-            // bit index formed in float (raymarching.cu:894): exact while below 2^24
-            const uint32_t bit = (uint32_t)__fadd_rn(__fmul_rn((float)level, mc.H3),
-                                                     (float)morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
-            occ = (__ldg(mc.bits + (bit >> 3)) >> (bit & 7)) & 1;
-        }
-        if (occ) {
+        if (march_cell(mc, g, h, t, x, y, z, dt, cost)) {
             t = __fadd_rn(t, dt);
             return true;
         }
-        // distance to the far face of this voxel along the ray (raymarching.cu:916-919)
-        const float fx = __fadd_rn(__fadd_rn((float)nx, 0.5f), __fmul_rn(0.5f, sx));
-        const float fy = __fadd_rn(__fadd_rn((float)ny, 0.5f), __fmul_rn(0.5f, sy));
-        const float fz = __fadd_rn(__fadd_rn((float)nz, 0.5f), __fmul_rn(0.5f, sz));
-        const float tx = __fmul_rn(__fsub_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(fx, mc.rH), 2.0f), 1.0f), mip_bound), x), g.rdx);
-        const float ty = __fmul_rn(__fsub_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(fy, mc.rH), 2.0f), 1.0f), mip_bound), y), g.rdy);
-        const float tz = __fmul_rn(__fsub_rn(__fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn(fz, mc.rH), 2.0f), 1.0f), mip_bound), z), g.rdz);
-        const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
-        do {
-            t = __fadd_rn(t, step_len(mc, t));
-        } while (t < tt);
     }
     return false;
+}
+
+// Resumable variant for prefetching: runs until a sample is found (returns 1, t = the sample's PRE-step parameter),
+// the ray is exhausted (0) or `budget` cost units are spent (2, t = resume point).  Splitting the loop across calls is
+// exact because every iteration is a pure function of t.
+__device__ __forceinline__ int march_budget(const MarchConst &mc, const RayGeom &g, float far, float &t, int &budget) {
+    MarchHoist h;
+    march_hoist(mc, g, h);
+    float x, y, z, dt;
+    while (t < far) {
+        if (budget <= 0) return 2;
+        int cost = 0;
+        const bool occ = march_cell(mc, g, h, t, x, y, z, dt, cost);
+        budget -= cost;
+        if (occ) return 1;
+    }
+    return 0;
+}
+
+// The emit step of the reference loop for a sample known to sit at parameter t_pre: position, step, t advanced past it.
+__device__ __forceinline__ void sample_at(const MarchConst &mc, const RayGeom &g, float t_pre, float &t, float &x, float &y,
+                                          float &z, float &dt) {
+    x = clampf(__fadd_rn(g.ox, __fmul_rn(t_pre, g.dx)), -mc.bound, mc.bound);
+    y = clampf(__fadd_rn(g.oy, __fmul_rn(t_pre, g.dy)), -mc.bound, mc.bound);
+    z = clampf(__fadd_rn(g.oz, __fmul_rn(t_pre, g.dz)), -mc.bound, mc.bound);
+    dt = step_len(mc, t_pre);
+    t = __fadd_rn(t_pre, dt);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -247,6 +297,70 @@ __device__ __forceinline__ float2 grid_lookup3(const GridMeta &gm, const float2 
         acc.y += wgt * c[i].y;
     }
     return acc;
+}
+
+// One x-half of the trilinear interpolation: the four (y,z) corners at x-cell gx + xbit, weighted.  The two lanes of a
+// pair (xbit 0/1) add their results.  Putting the two x-neighbours of a sample in ADJACENT LANES makes their 8-byte
+// entries (contiguous in the table) fall into one L1 wavefront: the gather is L1TEX-wavefront bound, and this halves the
+// wavefronts per sample (64 instead of 128 per table).
+__device__ __forceinline__ float2 grid_half3(const GridMeta &gm, const float2 *__restrict__ table, int l, float u, float v, float w,
+                                             int xbit) {
+    if (u < 0.f || u > 1.f || v < 0.f || v > 1.f || w < 0.f || w > 1.f) return make_float2(0.f, 0.f);
+    const float s = gm.scale[l];
+    float px = __fadd_rn(__fmul_rn(u, s), gm.align_off), py = __fadd_rn(__fmul_rn(v, s), gm.align_off),
+          pz = __fadd_rn(__fmul_rn(w, s), gm.align_off);
+    const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
+    const uint32_t gx = (uint32_t)fx0 + (uint32_t)xbit, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
+    px -= fx0; py -= fy0; pz -= fz0;
+    if (gm.interp == 1) {
+        px = px * px * (3.0f - 2.0f * px);
+        py = py * py * (3.0f - 2.0f * py);
+        pz = pz * pz * (3.0f - 2.0f * pz);
+    }
+    const float2 *tb = table + gm.offset[l];
+    float2 c[4];
+    if (!gm.hashed[l]) {
+        const uint32_t m1 = gm.mul1[l], m2 = gm.mul2[l], hm = gm.hmask[l], hs = gm.hsize[l];
+        const uint32_t base = gx + gy * m1 + gz * m2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t idx = base + ((i & 1) ? m1 : 0u) + ((i & 2) ? m2 : 0u);
+            if (hm) idx &= hm;
+            else if (idx >= hs) idx %= hs;
+            c[i] = __ldg(tb + idx);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[i] = __ldg(tb + grid_slot(gm, l, gx, gy + (i & 1), gz + ((i >> 1) & 1)));
+    }
+    const float wx = xbit ? px : 1.0f - px;
+    const float wy[2] = {1.0f - py, py}, wz[2] = {1.0f - pz, pz};
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float wgt = wx * wy[i & 1] * wz[(i >> 1) & 1];
+        acc.x += wgt * c[i].x;
+        acc.y += wgt * c[i].y;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float2 grid_half2(const GridMeta &gm, const float2 *__restrict__ table, int l, float u, float v, int xbit) {
+    if (u < 0.f || u > 1.f || v < 0.f || v > 1.f) return make_float2(0.f, 0.f);
+    const float s = gm.scale[l];
+    float px = __fadd_rn(__fmul_rn(u, s), gm.align_off), py = __fadd_rn(__fmul_rn(v, s), gm.align_off);
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const uint32_t gx = (uint32_t)fx0 + (uint32_t)xbit, gy = (uint32_t)fy0;
+    px -= fx0; py -= fy0;
+    if (gm.interp == 1) {
+        px = px * px * (3.0f - 2.0f * px);
+        py = py * py * (3.0f - 2.0f * py);
+    }
+    const float2 *tb = table + gm.offset[l];
+    const float2 c0 = __ldg(tb + grid_slot(gm, l, gx, gy, 0u)), c1 = __ldg(tb + grid_slot(gm, l, gx, gy + 1, 0u));
+    const float wx = xbit ? px : 1.0f - px;
+    const float w0 = wx * (1.0f - py), w1 = wx * py;
+    return make_float2(w0 * c0.x + w1 * c1.x, w0 * c0.y + w1 * c1.y);
 }
 
 __device__ __forceinline__ float2 grid_lookup2(const GridMeta &gm, const float2 *__restrict__ table, int l, float u,

@@ -22,6 +22,7 @@ __device__ __forceinline__ void warp_agg_add(int *base, int key, int val) {
 struct Slot {
     RayGeom g;
     float t, near, far, ws, depth, r, gch, b;
+    float far_m;   // marching bound: min(far, exit of the padded occupied box) -- nothing is occupied beyond it
     float px, py, pz, dt;  // pending sample
     int gid, frame, nsamp, cap;
     bool active;
@@ -48,8 +49,11 @@ __device__ __forceinline__ void load_ray(const HeadArgs &a, int frame, int ray, 
 }
 
 // conservative: can the segment [near, far] of the ray touch the (one-cell padded) box of occupied voxels?
+// On return `far_m` is the parameter beyond which the ray cannot meet an occupied voxel (<= far): the marcher may stop
+// there, which removes the long ALU-only walks of rays that have left the object.
 __device__ __forceinline__ bool may_hit_occupied(bool have_box, const float (&occ_lo)[3], const float (&occ_hi)[3],
-                                                 const RayGeom &g, float near, float far) {
+                                                 const RayGeom &g, float near, float far, float &far_m) {
+    far_m = far;
     if (!have_box) return true;
     float t0 = near, t1 = far;
     const float o[3] = {g.ox, g.oy, g.oz}, rd[3] = {g.rdx, g.rdy, g.rdz}, d[3] = {g.dx, g.dy, g.dz};
@@ -64,6 +68,7 @@ __device__ __forceinline__ bool may_hit_occupied(bool have_box, const float (&oc
         t0 = fmaxf(t0, ta);
         t1 = fminf(t1, tb);
     }
+    if (t0 <= t1) far_m = fminf(far, t1);
     return t0 <= t1;
 }
 
@@ -126,13 +131,83 @@ __device__ __forceinline__ bool march_next_nl(const MarchConst &mc, const RayGeo
 #endif
 }
 
+// ---- partner prefetch --------------------------------------------------------------------------------------------
+// Threads TM..2*TM-1 own no ray slot and used to idle while the owners composite.  Thread TM+i is the PARTNER of slot i:
+// during the composite phase it fetches candidate rays from the CTA's work chunk and marches them (a bounded number of
+// cell steps per round, resumable) until one reaches its first occupied sample, then parks {ray id, t_pre} in
+// s.spare_*[i].  When slot i dies, its owner adopts the spare in O(1) instead of marching a new ray while the whole CTA
+// waits at a barrier.  s.spare_gid codes: >= 0 ready, -1 empty (partner idle), -2 partner busy (will deliver).
+struct Partner {
+    RayGeom g;
+    float far, far_m, t;
+    int gid;
+    int state;   // 0 idle, 1 marching
+};
+constexpr int kPartnerBudget = 24;   // cost units per round: 4 per fine-bitfield read, 1 per ALU-only cell step
+
+template <class SmemT>
+__device__ __forceinline__ void partner_step(const HeadArgs &a, SmemT &s, Partner &p, const MarchConst &mc, bool have_box,
+                                             const float (&occ_lo)[3], const float (&occ_hi)[3], int tid) {
+    constexpr int TM = HEAD_TM;
+    if (tid < TM || a.pass != 1 || a.partner_budget <= 0) return;
+    const int i = tid - TM;
+    int budget = a.partner_budget;
+    while (budget > 0) {
+        if (p.state == 0) {
+            if (s.spare_gid[i] != -1 || s.next >= s.end) break;      // spare still parked, or no work in the local chunk
+            const int w = atomicAdd(&s.next, 1);
+            if (w >= s.end) break;
+            budget -= 2;
+            p.gid = w;
+            const int frame = w / a.n_rays, ray = w - frame * a.n_rays;
+            load_ray(a, frame, ray, p.g);
+            float near;
+            near_far(p.g, a.aabb, a.min_near, near, p.far);
+            p.t = near;
+            if (!may_hit_occupied(have_box, occ_lo, occ_hi, p.g, near, p.far, p.far_m)) {
+                // no sample at all: the ray dies at position 1 (delta == 0): zeros out, depth normalised like the reference
+                Slot z;
+                z.g = p.g; z.near = near; z.far = p.far; z.gid = w; z.frame = frame;
+                z.ws = 0.f; z.depth = 0.f; z.r = z.gch = z.b = 0.f;
+                finalize_ray(a, z, true);
+                warp_agg_add(a.hist, frame * (a.max_steps + 2) + 1, 1);
+                continue;
+            }
+            p.state = 1;
+            s.spare_gid[i] = -2;
+        }
+        const int r = march_budget(mc, p.g, p.far_m, p.t, budget);
+        if (r == 2) break;                                            // out of budget: resume next round
+        if (r == 1) {                                                 // found: park it
+            s.spare_t[i] = p.t;
+            s.spare_gid[i] = p.gid;
+            p.state = 0;
+            break;
+        }
+        // exhausted without a sample
+        {
+            const int frame = p.gid / a.n_rays;
+            Slot z;
+            z.g = p.g; z.far = p.far; z.gid = p.gid; z.frame = frame;
+            float nr, fr;
+            near_far(p.g, a.aabb, a.min_near, nr, fr);
+            z.near = nr;
+            z.ws = 0.f; z.depth = 0.f; z.r = z.gch = z.b = 0.f;
+            finalize_ray(a, z, true);
+            warp_agg_add(a.hist, frame * (a.max_steps + 2) + 1, 1);
+        }
+        p.state = 0;
+        s.spare_gid[i] = -1;
+    }
+}
+
 constexpr int kFetchTries = 4;   // rays a thread may try per refill iteration (most candidates are cheap misses)
 constexpr int kRefillIters = 2;
 
 // Refill dead slots from the global work cursor, then publish the batch (valid flags, frame ids, sample positions).
 // Returns the number of valid rows, or -1 when the CTA is out of work.  All threads of the CTA must call it.
 template <class SmemT>
-__device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, Slot &sl, const MarchConst &mc, bool have_box,
+__device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, Slot &sl, Partner &pt, const MarchConst &mc, bool have_box,
                                                   const float (&occ_lo)[3], const float (&occ_hi)[3], int total, int tid) {
     constexpr int TM = HEAD_TM;
     for (int it = 0; it < kRefillIters; ++it) {
@@ -142,12 +217,28 @@ __device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, S
             else { s.next = base; s.end = min(base + TM, total); }
         }
         __syncthreads();
-        if (tid < TM && !sl.active) {
+        if (tid < TM && !sl.active && s.spare_gid[tid] >= 0) {
+            // adopt the ray the partner thread pre-marched: O(1), no marching on the critical path
+            const int gid = s.spare_gid[tid];
+            sl.gid = gid;
+            sl.frame = gid / a.n_rays;
+            load_ray(a, sl.frame, gid - sl.frame * a.n_rays, sl.g);
+            near_far(sl.g, a.aabb, a.min_near, sl.near, sl.far);
+            (void)may_hit_occupied(have_box, occ_lo, occ_hi, sl.g, sl.near, sl.far, sl.far_m);
+            sl.ws = 0.f; sl.depth = 0.f; sl.r = sl.gch = sl.b = 0.f;
+            sl.nsamp = 0; sl.cap = a.max_steps;
+            sample_at(mc, sl.g, s.spare_t[tid], sl.t, sl.px, sl.py, sl.pz, sl.dt);
+            sl.active = true;
+            s.spare_gid[tid] = -1;
+        }
+        if (tid < TM && !sl.active && s.spare_gid[tid] == -1) {       // -2: the partner is about to deliver, just wait
             for (int attempt = 0; attempt < kFetchTries && !sl.active && s.next < s.end; ++attempt) {
                 const int w = atomicAdd(&s.next, 1);
                 if (w >= s.end) break;
-                int gid = w;
+                int gid;
+                float t_pre = 0.f;
                 if (a.pass == 2) gid = a.survivors[w];
+                else { const int2 hv = a.hits[w]; gid = hv.x; t_pre = __int_as_float(hv.y); }
                 sl.gid = gid;
                 sl.frame = gid / a.n_rays;
                 const int ray = gid - sl.frame * a.n_rays;
@@ -155,27 +246,26 @@ __device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, S
                 near_far(sl.g, a.aabb, a.min_near, sl.near, sl.far);
                 bool live;
                 if (a.pass == 1) {
-                    sl.t = sl.near; sl.ws = 0.f; sl.depth = 0.f; sl.r = sl.gch = sl.b = 0.f;
+                    // k_ray_setup already marched this ray to its first sample: adopt it in O(1)
+                    sl.ws = 0.f; sl.depth = 0.f; sl.r = sl.gch = sl.b = 0.f;
                     sl.nsamp = 0; sl.cap = a.max_steps;
-                    live = may_hit_occupied(have_box, occ_lo, occ_hi, sl.g, sl.near, sl.far) &&
-                           march_next_nl(mc, sl.g, sl.far, sl.t, sl.px, sl.py, sl.pz, sl.dt);
-                    if (!live) {  // no sample at all: the ray dies at position 1 (delta == 0)
-                        finalize_ray(a, sl, true);
-                        warp_agg_add(a.hist, sl.frame * (a.max_steps + 2) + 1, 1);
-                    }
+                    (void)may_hit_occupied(have_box, occ_lo, occ_hi, sl.g, sl.near, sl.far, sl.far_m);
+                    sample_at(mc, sl.g, t_pre, sl.t, sl.px, sl.py, sl.pz, sl.dt);
+                    live = true;
                 } else {
                     const size_t g = (size_t)gid;
                     sl.t = a.rays_t[g]; sl.ws = a.wsum[g]; sl.depth = a.depth[g];
                     sl.r = a.image[3 * g]; sl.gch = a.image[3 * g + 1]; sl.b = a.image[3 * g + 2];
                     sl.nsamp = a.max_steps; sl.cap = a.B_total[sl.frame];
-                    live = sl.nsamp < sl.cap && march_next_nl(mc, sl.g, sl.far, sl.t, sl.px, sl.py, sl.pz, sl.dt);
+                    (void)may_hit_occupied(have_box, occ_lo, occ_hi, sl.g, sl.near, sl.far, sl.far_m);
+                    live = sl.nsamp < sl.cap && march_next_nl(mc, sl.g, sl.far_m, sl.t, sl.px, sl.py, sl.pz, sl.dt);
                     if (!live) finalize_ray(a, sl, true);
                 }
                 sl.active = live;
             }
         }
         // another iteration only pays off when slots are still empty AND the local chunk ran dry while work remains
-        const int want_more = __syncthreads_or(tid < TM && !sl.active && s.next >= s.end && !s.done);
+        const int want_more = __syncthreads_or(tid < TM && !sl.active && s.spare_gid[tid] == -1 && s.next >= s.end && !s.done);
         if (!want_more) break;
     }
     if (tid < TM) {
@@ -185,9 +275,14 @@ __device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, S
     }
     const int n_valid = __syncthreads_count(tid < TM && sl.active);
     if (n_valid == 0) {
-        const bool out_of_work = s.done && s.next >= s.end;
+        // nothing to evaluate this round: finished only when the work is gone AND no partner still holds / marches a ray
+        const int pending = __syncthreads_count((tid < TM && s.spare_gid[tid] != -1) || (tid >= TM && pt.state != 0));
+        const bool out_of_work = s.done && s.next >= s.end && pending == 0;
         __syncthreads();  // thread 0 must not start the next refill (which rewrites next/end/done) before everyone has read them
-        return out_of_work ? -1 : 0;
+        if (out_of_work) return -1;
+        partner_step(a, s, pt, mc, have_box, occ_lo, occ_hi, tid);   // keep the prefetchers moving
+        __syncthreads();  // ... and finished before thread 0 may hand out the next chunk (they read next/end)
+        return 0;
     }
     return n_valid;
 }
@@ -195,8 +290,10 @@ __device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, S
 // Front-to-back compositing of the batch's sample in the owner thread (raymarching.cu:978-1006), termination test,
 // then march to the ray's next sample (or retire the ray).
 template <class SmemT>
-__device__ __forceinline__ void composite_and_advance(const HeadArgs &a, SmemT &s, Slot &sl, const MarchConst &mc, int tid) {
+__device__ __forceinline__ void composite_and_advance(const HeadArgs &a, SmemT &s, Slot &sl, Partner &pt, const MarchConst &mc,
+                                                      bool have_box, const float (&occ_lo)[3], const float (&occ_hi)[3], int tid) {
     constexpr int TM = HEAD_TM;
+    partner_step(a, s, pt, mc, have_box, occ_lo, occ_hi, tid);
     if (tid < TM && sl.active) {
         const float sigma = s.sig[tid];
         const float alpha = 1.0f - expf(-sigma * sl.dt);
@@ -213,7 +310,7 @@ __device__ __forceinline__ void composite_and_advance(const HeadArgs &a, SmemT &
         bool suspend = false;
         if (T < a.T_thresh) D = sl.nsamp;
         else if (sl.nsamp >= sl.cap) suspend = true;
-        else if (!march_next_nl(mc, sl.g, sl.far, sl.t, sl.px, sl.py, sl.pz, sl.dt)) D = sl.nsamp + 1;
+        else if (!march_next_nl(mc, sl.g, sl.far_m, sl.t, sl.px, sl.py, sl.pz, sl.dt)) D = sl.nsamp + 1;
         if (D) {
             finalize_ray(a, sl, true);
             if (a.pass == 1) warp_agg_add(a.hist, sl.frame * (a.max_steps + 2) + D, 1);

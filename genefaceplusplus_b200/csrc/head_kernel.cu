@@ -53,6 +53,8 @@ struct Smem {
     int valid[TM];
     unsigned long long bar[NSTAGE];
     uint32_t coarse[HEAD_COARSE_WORDS];
+    int spare_gid[HEAD_TM];   // partner prefetch hand-off (head_common.cuh)
+    float spare_t[HEAD_TM];
     int next, end, done;
 };
 
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ Hea
     float occ_lo[3] = {0.f, 0.f, 0.f}, occ_hi[3] = {0.f, 0.f, 0.f};
     const bool have_box = setup_occupancy(a, mc, occ_lo, occ_hi);
     install_coarse(a, s, mc, tid, NT);
+    if (tid < TM) s.spare_gid[tid] = -1;
     for (int i = tid; i < 8 * 128; i += NT) s.narrow[i] = a.narrow[i];
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) mbar_init(&s.bar[i], 1);
@@ -221,14 +224,16 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ Hea
     WStream wst;
     wst.consumed = 0;
 
-    const int total = (a.pass == 1) ? a.n_frames * a.n_rays : *a.n_survivors;
+    const int total = (a.pass == 1) ? *a.n_hits : *a.n_survivors;
     Slot sl;
     sl.active = false;
     sl.gid = 0; sl.frame = 0; sl.nsamp = 0; sl.cap = 0;
+    Partner pt;
+    pt.state = 0; pt.gid = 0; pt.t = 0.f; pt.far = 0.f;
 
     for (;;) {
         // ================= refill dead slots from the global cursor, publish the batch (head_common.cuh) =================
-        const int n_valid = refill_and_publish(a, s, sl, mc, have_box, occ_lo, occ_hi, total, tid);
+        const int n_valid = refill_and_publish(a, s, sl, pt, mc, have_box, occ_lo, occ_hi, total, tid);
         if (n_valid < 0) break;
         if (n_valid == 0) continue;
 
@@ -363,7 +368,7 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ Hea
         __syncthreads();
 
         // ================= composite + advance (head_common.cuh) =================
-        composite_and_advance(a, s, sl, mc, tid);
+        composite_and_advance(a, s, sl, pt, mc, have_box, occ_lo, occ_hi, tid);
         // no barrier needed here: the refill starts with one before shared memory is touched again
     }
 
@@ -371,6 +376,41 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ Hea
     for (uint32_t q = 0; q < NSTAGE; ++q) {
         const uint32_t seq = wst.consumed + q;
         mbar_wait(&s.bar[seq % NSTAGE], (seq / NSTAGE) & 1);
+    }
+}
+
+// Ray setup: one thread per (frame, ray).  Generates / loads the ray, slab-tests it, and marches it to its FIRST occupied
+// sample with full occupancy (64 warps/SM hide the dependent bitfield reads).  Rays without any sample (57 % of a
+// talking-head frame) are finished here: zero colour/alpha, normalised depth, death index 1.  The others are appended to
+// the hit list {ray id, t_pre}; the persistent head kernel adopts them in O(1), so no first-hit marching ever sits
+// between two CTA barriers of the MLP pipeline.
+__global__ void __launch_bounds__(256) k_ray_setup(const __grid_constant__ HeadArgs a) {
+    MarchConst mc = a.mc;
+    float occ_lo[3] = {0.f, 0.f, 0.f}, occ_hi[3] = {0.f, 0.f, 0.f};
+    const bool have_box = setup_occupancy(a, mc, occ_lo, occ_hi);
+    mc.coarse = a.coarse_bits;
+    const int total = a.n_frames * a.n_rays;
+    for (int gid = blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += gridDim.x * blockDim.x) {
+        Slot sl;
+        sl.gid = gid;
+        sl.frame = gid / a.n_rays;
+        load_ray(a, sl.frame, gid - sl.frame * a.n_rays, sl.g);
+        near_far(sl.g, a.aabb, a.min_near, sl.near, sl.far);
+        sl.t = sl.near;
+        int budget = 1 << 30;
+        const bool hit = may_hit_occupied(have_box, occ_lo, occ_hi, sl.g, sl.near, sl.far, sl.far_m) &&
+                         march_budget(mc, sl.g, sl.far_m, sl.t, budget) == 1;
+        if (hit) {
+            cg::coalesced_group grp = cg::coalesced_threads();
+            int base = 0;
+            if (grp.thread_rank() == 0) base = atomicAdd(a.n_hits, (int)grp.size());
+            base = grp.shfl(base, 0);
+            a.hits[base + grp.thread_rank()] = make_int2(gid, __float_as_int(sl.t));
+        } else {
+            sl.ws = 0.f; sl.depth = 0.f; sl.r = sl.gch = sl.b = 0.f;
+            finalize_ray(a, sl, true);
+            warp_agg_add(a.hist, sl.frame * (a.max_steps + 2) + 1, 1);
+        }
     }
 }
 
@@ -407,6 +447,12 @@ cudaError_t launch_head(const HeadArgs &a, int total_hint, cudaStream_t st) {
         if (need < blocks) blocks = need > 0 ? need : 1;
     }
     k_head<<<blocks, NT, sizeof(Smem), st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ray_setup(const HeadArgs &a, cudaStream_t st) {
+    const uint64_t total = (uint64_t)a.n_frames * a.n_rays;
+    k_ray_setup<<<grid_for(total, 256), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

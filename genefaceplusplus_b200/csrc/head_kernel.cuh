@@ -39,12 +39,16 @@ struct HeadArgs {
     float *depth;                   // [F,N]
     float *rays_t;                  // [F,N] resume point of rays that outlive max_steps
     int *hist;                      // [F, max_steps+2] death-index histogram
+    int2 *hits;                     // [F*N] (ray id, bits of t_pre): rays that reach a first sample, from k_ray_setup
+    int *n_hits;                    // [1]
     int *survivors;                 // [F*N] global ray ids still alive after max_steps samples
     int *n_survivors;               // [1]
     int *cursor;                    // [1] global work cursor
     int *B_total;                   // [F] per-frame sample cap produced by k_schedule
     int *valid_samples;             // [F] statistics (or nullptr)
     int pass;                       // 1 or 2
+    unsigned long long *phase_cycles;  // optional [32]: per-phase cycle totals of thread 0 of every CTA (diagnostics)
+    int partner_budget;             // per-round prefetch budget of the partner threads (0 = prefetch off)
 };
 
 // tensor-core variant: pre-swizzled 16-bit weight tiles (see pack_tc_weights in capi.cu)
@@ -62,6 +66,7 @@ size_t head_tc_smem_bytes(bool split);
 
 size_t head_smem_bytes();
 cudaError_t launch_head(const HeadArgs &a, int total_hint, cudaStream_t st);
+cudaError_t launch_ray_setup(const HeadArgs &a, cudaStream_t st);
 cudaError_t launch_schedule(const int *hist, int n_frames, int n_rays, int max_steps, int *B_total, cudaStream_t st);
 
 }  // namespace gfpp

@@ -61,6 +61,8 @@ struct SmemTC {
     unsigned long long bar_acc;
     uint32_t tmem_base;
     uint32_t coarse[HEAD_COARSE_WORDS];
+    int spare_gid[HEAD_TM];   // partner prefetch hand-off (head_common.cuh)
+    float spare_t[HEAD_TM];
     int next, end, done;
 };
 
@@ -146,7 +148,7 @@ __device__ __noinline__ void epilogue_wide(unsigned char *a_hi, unsigned char *a
     }
 }
 
-// Four consecutive levels of a 3-D (or 2-D) grid -> 8 features (one 16-byte operand chunk).  Out of line on purpose.
+// Four consecutive levels of a grid -> 8 features (one 16-byte operand chunk).  Out of line on purpose (I-cache).
 __device__ __noinline__ void lookup4(const GridMeta &gm, const float2 *__restrict__ table, int l0, float u, float v, float w, float (&f)[8]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -163,13 +165,14 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
     extern __shared__ __align__(1024) unsigned char smem_raw_[];
     unsigned char *smem_raw = smem_raw_ + ((1024u - (smem_u32(smem_raw_) & 1023u)) & 1023u);
     SmemTC<SPLIT> &s = *reinterpret_cast<SmemTC<SPLIT> *>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- one-time setup ----
     MarchConst mc = a.mc;
     float occ_lo[3] = {0.f, 0.f, 0.f}, occ_hi[3] = {0.f, 0.f, 0.f};
     const bool have_box = setup_occupancy(a, mc, occ_lo, occ_hi);
     install_coarse(a, s, mc, tid, NT);
+    if (tid < TM) s.spare_gid[tid] = -1;
     if (warp == 0) tmem_alloc(&s.tmem_base, TMEM_COLS);
     if (tid == 32) {
         for (int i = 0; i < W_NSTAGE; ++i) mbar_init(&s.bar_full[i], 1);
@@ -195,16 +198,26 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
     const uint32_t idesc128 = make_idesc(BF16 ? 1 : 0, 128), idesc144 = make_idesc(BF16 ? 1 : 0, 144), idesc16 = make_idesc(BF16 ? 1 : 0, 16);
     const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
 
-    const int total = (a.pass == 1) ? a.n_frames * a.n_rays : *a.n_survivors;
+    const int total = (a.pass == 1) ? *a.n_hits : *a.n_survivors;
     Slot sl;
     sl.active = false;
     sl.gid = 0; sl.frame = 0; sl.nsamp = 0; sl.cap = 0;
+    Partner pt;
+    pt.state = 0; pt.gid = 0; pt.t = 0.f; pt.far = 0.f;
 
+    long long ph_last = clock64();
+#define PH(i)                                                                                   \
+    if (a.phase_cycles && tid == 0) {                                                           \
+        const long long now_ = clock64();                                                       \
+        atomicAdd(a.phase_cycles + (i), (unsigned long long)(now_ - ph_last));                  \
+        ph_last = now_;                                                                         \
+    }
     for (;;) {
         // ================= refill dead slots from the global cursor, publish the batch (head_common.cuh) =================
-        const int n_valid = refill_and_publish(a, s, sl, mc, have_box, occ_lo, occ_hi, total, tid);
+        const int n_valid = refill_and_publish(a, s, sl, pt, mc, have_box, occ_lo, occ_hi, total, tid);
         if (n_valid < 0) break;
         if (n_valid == 0) continue;
+        PH(0)   // refill + publish
 
         const int slot = tid & (TM - 1), lg = tid >> 7;
         const bool v = s.valid[slot] != 0;
@@ -247,16 +260,21 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
+        PH(1)   // position gather + cond + park
 
         // ---- ambient net 96 -> 128 -> 128 -> 3 ----
         if (tid == 0) issue_layer<SPLIT>(t, s, st, 2, tmem, idesc128);
         wait_acc<SPLIT>(t, s, st, 2, tid);
+        PH(2)   // MMA issue + wait (ambient L0)
         epilogue_wide<BF16, SPLIT, true, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr);
         fence_async_smem(); fence_before_sync(); __syncthreads();
+        PH(3)   // epilogue (ambient L0) + barrier
         if (tid == 0) issue_layer<SPLIT>(t, s, st, 2, tmem, idesc128);
         wait_acc<SPLIT>(t, s, st, 2, tid);
+        PH(4)   // MMA (ambient L1)
         epilogue_wide<BF16, SPLIT, true, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr);
         fence_async_smem(); fence_before_sync(); __syncthreads();
+        PH(5)   // epilogue (ambient L1)
         if (tid == 0) issue_narrow<SPLIT>(s, 0, tmem, idesc16);
         wait_acc<SPLIT>(t, s, st, 0, tid);
         if (tid < TM) {
@@ -270,6 +288,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
         fence_before_sync();
         __syncthreads();
         fence_after_sync();
+        PH(6)   // narrow ambient out: MMA + tanh
         // ---- sigma-net input: tile0 k[0,32) <- parked position features, k[32,64) <- ambient grid ----
         {
             float u = 0.f, vv = 0.f, w = 0.f;
@@ -293,6 +312,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
             }
         }
         fence_async_smem(); fence_before_sync(); __syncthreads();
+        PH(7)   // ambient gather + unpark
 
         // ---- sigma net 64 -> 128 -> 128 -> (128 geo + sigma) ----
         if (tid == 0) issue_layer<SPLIT>(t, s, st, 1, tmem, idesc128);
@@ -323,6 +343,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
         epilogue_wide<BF16, SPLIT, false, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr);   // geo features -> tiles 0,1 (k = 0..127)
         fence_async_smem(); fence_before_sync(); __syncthreads();
 
+        PH(8)   // sigma net: 3 MMA layers + 3 epilogues
         // ---- color net (128 geo + 16 SH [+ folded individual code]) -> 128 -> 3 ----
         if (tid == 0) issue_layer<SPLIT>(t, s, st, 3, tmem, idesc128);
         wait_acc<SPLIT>(t, s, st, 3, tid);
@@ -342,8 +363,11 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
         __syncthreads();
         fence_after_sync();
 
+        PH(9)   // color net: 2 MMA layers + epilogue + sigmoid
         // ================= composite + advance (head_common.cuh) =================
-        composite_and_advance(a, s, sl, mc, tid);
+        composite_and_advance(a, s, sl, pt, mc, have_box, occ_lo, occ_hi, tid);
+        PH(10)  // composite + march to next sample
+        if (a.phase_cycles && tid == 0) atomicAdd(a.phase_cycles + 31, 1ull);   // batches
         // no barrier needed here: the refill starts with one before shared memory is touched again
     }
 

@@ -189,6 +189,9 @@ GFPP_API int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fram
  * most recent call in milliseconds: ms[0] = head pass 1, ms[1] = schedule + head pass 2, ms[2] = torso/composite epilogue. */
 GFPP_API int gfpp_profile_enable(int on);
 GFPP_API int gfpp_profile_read(float ms[3]);
+/* optional: device buffer of 32 uint64 that the tensor-core head kernel fills with per-phase cycle totals (thread 0 of each
+ * CTA; slot 31 = batches processed); NULL switches it off.  Diagnostics only. */
+GFPP_API int gfpp_profile_phases(void *dev_u64x32);
 /* Self-test of the tcgen05 plumbing (tile layouts, descriptors, MMA issue, TMEM read-back) used by the tensor-core MLP:
  * out[128,N] = A[128,K] @ W[N,K]^T with 16-bit operands, fp32 accumulation.  K = 64*j (+16 if k16_tail), N % 16 == 0,
  * N <= 144, K <= 144.  precision: 1 = fp16, 2 = bf16 hi/lo split (3 MMAs), 3 = bf16.  scratch: >= 6*18432 bytes. */

@@ -101,7 +101,10 @@ def test_grid_encoder_vs_reference_kernel(oracle_ops, D):
     ge.grid_encode_forward(x.cuda(), emb.cuda(), off.cuda(), out, 8192, D, 2, 16, float(np.log2(lay.per_level_scale)), 16, None, 1, False, 0)
     d = (out.permute(1, 0, 2).reshape(8192, 32).cpu() - ref).abs().max().item()
     print(f"grid D={D}: max |reference kernel - C oracle| = {d:.2e}")
-    assert d <= 5e-6
+    # The reference kernel derives each level scale with the DEVICE exp2f (gridencoder.cu:137; <= 2 ulp, MUFU.EX2 based); the
+    # oracle and libgfpp use the host libm exp2f.  A 1-ulp difference in a scale of ~2047 moves the finest-level sample
+    # position by ~1e-4 cells, i.e. up to ~2e-4 in a feature for U(-0.5,0.5) tables.  Bounded here, documented in DESIGN.md.
+    assert d <= 5e-4
 
 
 def test_sh_and_freq_vs_reference_kernels(oracle_ops):
