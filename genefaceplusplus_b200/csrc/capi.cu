@@ -24,6 +24,7 @@ cudaError_t launch_sh_encode(const float *, float *, uint32_t, uint32_t, cudaStr
 cudaError_t launch_freq_encode(const float *, uint32_t, uint32_t, uint32_t, float *, cudaStream_t);
 cudaError_t launch_occupancy_bounds(const uint8_t *, uint32_t, uint32_t, int *, cudaStream_t);
 cudaError_t launch_coarse_occupancy(const uint8_t *, uint32_t, uint32_t, uint32_t *, cudaStream_t);
+cudaError_t launch_pack_quads(const GridMeta &, const float *, float *, uint32_t, cudaStream_t);
 // tc_pack.cu
 cudaError_t launch_pack_tc_tile(const float *, int, int, int, int, int, int, int, int, unsigned char *, unsigned char *, cudaStream_t);
 cudaError_t launch_tc_selftest(const float *, int, const unsigned char *, const unsigned char *, int, int, int, int, float *, cudaStream_t);
@@ -67,6 +68,7 @@ int fill_grid_meta(GridMeta &gm, const int32_t *offsets, uint32_t D, uint32_t L,
     gm.dim = D;
     gm.interp = interp;
     gm.align_off = align_corners ? 0.0f : 0.5f;
+    bool quad_ok = true;
     for (uint32_t l = 0; l < L; ++l) {
         const float scale = exp2f((float)l * S) * (float)H - 1.0f;
         const uint32_t res = (uint32_t)ceil((double)scale) + 1;
@@ -86,7 +88,11 @@ int fill_grid_meta(GridMeta &gm, const int32_t *offsets, uint32_t D, uint32_t L,
         gm.mul1[l] = mul[1];
         gm.mul2[l] = mul[2];
         gm.hashed[l] = (gridtype == 0 && stride > hs) ? 1u : 0u;
+        // the packed-corner layout needs corner slots = base + const offsets, consistently under the level's modulo
+        const unsigned long long span = (unsigned long long)(res + 1) * (1ull + mul[1] + mul[2]);
+        if (gm.hashed[l] || (gm.hmask[l] == 0 && span >= (1ull << 32))) quad_ok = false;
     }
+    gm.quad_ok = quad_ok ? 1u : 0u;
     return 0;
 }
 
@@ -98,6 +104,7 @@ struct ModelHost {
     int has_torso;
     GridMeta pos_gm, amb_gm, tor_gm;
     const float2 *pos_tab, *amb_tab, *tor_tab;
+    const float4 *pos_quads, *amb_quads;
     const uint8_t *bitfield;
     const float *density_grid_torso;
     const float *torso_def0_src, *torso_can0_src, *torso_code;  // originals (per-frame bias fold reads them)
@@ -120,7 +127,7 @@ static_assert(sizeof(ModelHost) <= sizeof(gfpp_model), "gfpp_model opaque storag
 constexpr uint32_t kMagic = 0x67667070u;  // "gfpp"
 
 struct PackedLayout {
-    size_t wide, narrow, wd0, wd1, wd2, wc0, wc1, wc2, occ, coarse, tc_hi, tc_lo, tcn_hi, tcn_lo, total;
+    size_t wide, narrow, wd0, wd1, wd2, wc0, wc1, wc2, occ, coarse, tc_hi, tc_lo, tcn_hi, tcn_lo, pos_quads, amb_quads, total;
 };
 
 // tensor-core weight stream: 12 tiles per batch (see head_tc_kernel.cu)
@@ -140,7 +147,7 @@ inline size_t coarse_words_for(uint32_t cascade, uint32_t grid_size) {
     return (cascade * hc * hc * hc + 31) / 32;
 }
 
-PackedLayout packed_layout(uint32_t cascade = 8, uint32_t grid_size = 128) {
+PackedLayout packed_layout(uint32_t cascade = 8, uint32_t grid_size = 128, size_t pos_entries = 0, size_t amb_entries = 0) {
     PackedLayout L;
     size_t o = 0;
     auto take = [&](size_t floats) { size_t r = o; o += (floats * 4 + 255) / 256 * 256; return r; };
@@ -162,6 +169,8 @@ PackedLayout packed_layout(uint32_t cascade = 8, uint32_t grid_size = 128) {
     L.tc_lo = take(tcb / 4);
     L.tcn_hi = take(4 * 2048 / 4);
     L.tcn_lo = take(4 * 2048 / 4);
+    L.pos_quads = take(pos_entries * 8);   // 32 bytes per entry
+    L.amb_quads = take(amb_entries * 8);
     L.total = o;
     return L;
 }
@@ -343,14 +352,21 @@ int gfpp_tc_selftest(const float *A, const float *W, uint32_t N, uint32_t K, int
 // ------------------------------------------------------------------ (B) fused renderer
 size_t gfpp_model_packed_bytes(const gfpp_model_desc *desc) {
     if (!desc) return packed_layout().total;
-    return packed_layout(desc->cascade, desc->grid_size).total;
+    const gfpp_grid_desc &p = desc->position_grid, &q = desc->ambient_grid;
+    const size_t pe = p.offsets_host && p.num_levels <= 16 ? (size_t)p.offsets_host[p.num_levels] : 0;
+    const size_t ae = q.offsets_host && q.num_levels <= 16 ? (size_t)q.offsets_host[q.num_levels] : 0;
+    return packed_layout(desc->cascade, desc->grid_size, pe, ae).total;
 }
 
 int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes, gfpp_model *model, void *stream) {
     if (!d || !packed || !model) return fail(GFPP_ERR_INVALID, "model_pack: null pointer%s");
     if (d->cascade < 1 || d->cascade > 8 || d->grid_size < 8 || d->grid_size > 1024 || d->grid_size % 4)
         return fail(GFPP_ERR_UNSUPPORTED, "model_pack: cascade/grid_size out of range%s");
-    const PackedLayout L = packed_layout(d->cascade, d->grid_size);
+    if (!d->position_grid.offsets_host || !d->ambient_grid.offsets_host || d->position_grid.num_levels > 16 || d->ambient_grid.num_levels > 16)
+        return fail(GFPP_ERR_INVALID, "model_pack: grid offsets missing%s");
+    const size_t pos_entries = (size_t)d->position_grid.offsets_host[d->position_grid.num_levels];
+    const size_t amb_entries = (size_t)d->ambient_grid.offsets_host[d->ambient_grid.num_levels];
+    const PackedLayout L = packed_layout(d->cascade, d->grid_size, pos_entries, amb_entries);
     if (packed_bytes < L.total) return fail(GFPP_ERR_WORKSPACE, "model_pack: packed buffer too small%s");
     if (d->cond_dim != 64 || d->ind_dim > 16) return fail(GFPP_ERR_UNSUPPORTED, "model_pack: cond_dim must be 64, ind_dim <= 16%s");
     if (d->cascade < 1 || d->cascade > 8 || d->grid_size < 8 || d->grid_size > 1024)
@@ -428,6 +444,9 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
     CK(launch_coarse_occupancy(d->density_bitfield, d->cascade, d->grid_size, coarse, st));
     m.coarse_bits = coarse;
 
+    // sector-packed corner copies of the two head grids (tiled layouts only); done before the tensor-core weight
+    // packing below because that one clears everything from tc_hi to the END of the packed buffer
+    const bool want_quads = getenv("GFPP_NO_QUADS") == nullptr;
     m.mlp_precision = (int)d->mlp_precision;
     if (d->mlp_precision > 3) return fail(GFPP_ERR_UNSUPPORTED, "model_pack: mlp_precision must be 0..3%s");
     if (d->mlp_precision != 0) {
@@ -435,7 +454,7 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
         const bool split = d->mlp_precision == 2;
         unsigned char *thi = (unsigned char *)(base + L.tc_hi), *tlo = (unsigned char *)(base + L.tc_lo);
         unsigned char *nhi = (unsigned char *)(base + L.tcn_hi), *nlo = (unsigned char *)(base + L.tcn_lo);
-        CKN(cudaMemsetAsync(base + L.tc_hi, 0, L.total - L.tc_hi, st));
+        CKN(cudaMemsetAsync(base + L.tc_hi, 0, L.pos_quads - L.tc_hi, st));
         const float *lw[6] = {d->ambient_w[0], d->ambient_w[1], d->sigma_w[0], d->sigma_w[1], d->sigma_w[2], d->color_w[0]};
         const int lld[6] = {96, 128, 64, 128, 128, col0_in};
         int boff = 0;
@@ -458,6 +477,15 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
             CK(launch_pack_tc_tile(d->color_w[1], 128, 0, kt * 64, 3, 64, 0, 0, bf16, nhi + (2 + kt) * 2048, split ? nlo + (2 + kt) * 2048 : nullptr, st));
         }
         m.tc.w_hi = thi; m.tc.w_lo = tlo; m.tc.narrow_hi = nhi; m.tc.narrow_lo = nlo;
+    }
+
+    if (want_quads && m.pos_gm.quad_ok && m.pos_gm.dim == 3) {
+        CK(launch_pack_quads(m.pos_gm, d->position_grid.embeddings, (float *)(base + L.pos_quads), (uint32_t)pos_entries, st));
+        m.pos_quads = (const float4 *)(base + L.pos_quads);
+    }
+    if (want_quads && m.amb_gm.quad_ok && m.amb_gm.dim == 3) {
+        CK(launch_pack_quads(m.amb_gm, d->ambient_grid.embeddings, (float *)(base + L.amb_quads), (uint32_t)amb_entries, st));
+        m.amb_quads = (const float4 *)(base + L.amb_quads);
     }
 
     m.has_torso = d->has_torso;
@@ -518,6 +546,7 @@ int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfp
     memset(&a, 0, sizeof(a));
     a.pos_gm = m.pos_gm; a.amb_gm = m.amb_gm;
     a.pos_tab = m.pos_tab; a.amb_tab = m.amb_tab;
+    a.pos_quads = m.pos_quads; a.amb_quads = m.amb_quads;
     a.wide = m.wide; a.narrow = m.narrow;
     for (int c = 0; c < HEAD_NCHUNK; ++c) { a.chunk_off[c] = m.chunk_off[c]; a.chunk_k[c] = kChunkK[c]; }
     march_const_init(a.mc, m.bound, fr->dt_gamma, fr->max_steps, m.cascade, m.grid_size, m.bitfield);

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ Hea
                 const float w = __fdiv_rn(__fadd_rn(s.sz[slot], mc.bound), inv2b);
 #pragma unroll 2
                 for (int l = lg * 8; l < lg * 8 + 8; ++l) {
-                    const float2 f = grid_lookup3(a.pos_gm, a.pos_tab, l, u, vv, w);
+                    const float2 f = a.pos_quads ? grid_lookup3q(a.pos_gm, a.pos_quads, l, u, vv, w) : grid_lookup3(a.pos_gm, a.pos_tab, l, u, vv, w);
                     *reinterpret_cast<float2 *>(ar + 2 * l) = f;
                     *reinterpret_cast<float2 *>(pr + 2 * l) = f;
                 }
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ Hea
                 const float w = __fdiv_rn(__fadd_rn(s.amb[2 * TM + slot], 1.0f), 2.0f);
 #pragma unroll 2
                 for (int l = lg * 8; l < lg * 8 + 8; ++l) {
-                    const float2 f = (a.amb_gm.dim == 3) ? grid_lookup3(a.amb_gm, a.amb_tab, l, u, vv, w)
+                    const float2 f = (a.amb_gm.dim == 3) ? (a.amb_quads ? grid_lookup3q(a.amb_gm, a.amb_quads, l, u, vv, w) : grid_lookup3(a.amb_gm, a.amb_tab, l, u, vv, w))
                                                          : grid_lookup2(a.amb_gm, a.amb_tab, l, u, vv);
                     *reinterpret_cast<float2 *>(ar + 32 + 2 * l) = f;
                 }

@@ -13,6 +13,7 @@ struct HeadArgs {
     // ---- model ----
     GridMeta pos_gm, amb_gm;
     const float2 *pos_tab, *amb_tab;
+    const float4 *pos_quads, *amb_quads;   // sector-packed corner layout (nullptr: use the reference layout)
     const float *wide;              // concatenated k-major weight chunks, stream order
     int chunk_off[HEAD_NCHUNK];     // float offset of each chunk in `wide`
     int chunk_k[HEAD_NCHUNK];       // k-rows in each chunk (<= 72, multiple of 4)

@@ -182,7 +182,28 @@ __global__ void k_coarse_occupancy(const uint8_t *__restrict__ bits, uint32_t C,
     }
 }
 
+// ---- sector-packed corner layout of a tiled grid (common.cuh: grid_lookup3q) ----
+__global__ void k_pack_quads(GridMeta gm, const float2 *__restrict__ table, float4 *__restrict__ quads, uint32_t total) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int l = 0;
+#pragma unroll 1
+        for (int k = 1; k < (int)gm.num_levels; ++k)
+            if (i >= gm.offset[k]) l = k;
+        const uint32_t q = i - gm.offset[l], m1 = gm.mul1[l];
+        const float2 *tb = table + gm.offset[l];
+        const float2 e0 = tb[grid_mod(gm, l, q)], e1 = tb[grid_mod(gm, l, q + 1)], e2 = tb[grid_mod(gm, l, q + m1)],
+                     e3 = tb[grid_mod(gm, l, q + m1 + 1)];
+        quads[2 * (size_t)i] = make_float4(e0.x, e0.y, e1.x, e1.y);
+        quads[2 * (size_t)i + 1] = make_float4(e2.x, e2.y, e3.x, e3.y);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
+cudaError_t launch_pack_quads(const GridMeta &gm, const float *table, float *quads, uint32_t total, cudaStream_t st) {
+    k_pack_quads<<<grid_for(total, 256), 256, 0, st>>>(gm, (const float2 *)table, (float4 *)quads, total);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_coarse_occupancy(const uint8_t *bits, uint32_t C, uint32_t H, uint32_t *coarse, cudaStream_t st) {
     const uint32_t Hc = H / 4;
     k_coarse_occupancy<<<grid_for((uint64_t)C * Hc * Hc * Hc, 256), 256, 0, st>>>(bits, C, H, coarse);

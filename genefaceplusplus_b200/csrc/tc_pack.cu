@@ -96,7 +96,10 @@ __global__ void __launch_bounds__(256, 1) k_tc_selftest(const float *__restrict_
         const uint32_t idesc = make_idesc(BF16 ? 1 : 0, N);
         for (int t = 0; t < ntiles; ++t) {
             const bool is16 = k16_tail && t == nt64;
-            issue_ktile(tmem, smem_u32(s.a_hi[t]), smem_u32(s.a_lo[t]), smem_u32(s.w_hi[t]), smem_u32(s.w_lo[t]), is16 ? 1 : 4, is16,
+            // a partial last 64-wide tile only holds (K - 64*t)/16 k-steps of defined operand data
+            const int k64 = K - (k16_tail ? 16 : 0);
+            const int ks = is16 ? 1 : ((k64 - 64 * t) >= 64 ? 4 : (k64 - 64 * t) / 16);
+            issue_ktile(tmem, smem_u32(s.a_hi[t]), smem_u32(s.a_lo[t]), smem_u32(s.w_hi[t]), smem_u32(s.w_lo[t]), ks, is16,
                         SPLIT, idesc, t > 0);
         }
         mma_commit(&s.bar_acc);
