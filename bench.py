@@ -286,17 +286,17 @@ def main():
 
     # ---------------- dominant-kernel roofline (live, CUDA events inside libgfpp) ----------------
     L.gfpp_profile_enable(1)
-    head_ms, pass2_ms, epi_ms = [], [], []
+    head_ms, pass2_ms, epi_ms, pre_ms = [], [], [], []
     feat = model.cal_cond_feat_clip(cond_dev)[s:e]
     Fc = min(args.frames_per_call, T)
     for it in range(5):
         model.render_frames(feat[:Fc], poses_c2w=poses_dev[:Fc], intrinsics=sc.intrinsics, H=H, W=W,
                             pose6=pose6_dev[:Fc] if not args.head_only else None, bg_coords=bg_coords, bg_color=bg_color,
                             dt_gamma=sc.hparams["dt_gamma"], max_steps=sc.hparams["max_steps"], T_thresh=sc.T_thresh, want_torso_maps=False)
-        buf = (ctypes.c_float * 3)()
+        buf = (ctypes.c_float * 4)()
         _capi.check(L.gfpp_profile_read(buf), "profile_read")
         if it >= 2:
-            head_ms.append(buf[0]); pass2_ms.append(buf[1]); epi_ms.append(buf[2])
+            head_ms.append(buf[0]); pass2_ms.append(buf[1]); epi_ms.append(buf[2]); pre_ms.append(buf[3])
     L.gfpp_profile_enable(0)
     hbm, peak_kind, _ = peaks()
     head_t = statistics.mean(head_ms) / 1000.0
@@ -307,7 +307,8 @@ def main():
     achieved = alg_bytes / head_t / 1e9
     roofline = {"bound": "hbm", "kernel": "k_head (pass 1)" if args.precision == "fp32" else "k_head_tc (pass 1)", "achieved": achieved, "peak": hbm, "peak_source": peak_kind, "unit": "GB/s",
                 "frac": achieved / hbm, "traffic": None, "launch_ms": head_t * 1000.0, "frames_per_launch": Fc,
-                "share_of_step": head_t / (head_t + statistics.mean(pass2_ms) / 1000 + statistics.mean(epi_ms) / 1000),
+                "share_of_step": head_t / (head_t + (statistics.mean(pass2_ms) + statistics.mean(epi_ms) + statistics.mean(pre_ms)) / 1000),
+                "ray_setup_ms": statistics.mean(pre_ms),
                 "fp32_tflops": alg_flops / head_t / 1e12, "pass2_ms": statistics.mean(pass2_ms), "epilogue_ms": statistics.mean(epi_ms),
                 "alg_bytes_per_frame": alg_bytes / Fc, "alg_flops_per_frame": alg_flops / Fc}
 

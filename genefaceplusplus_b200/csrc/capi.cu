@@ -38,7 +38,7 @@ thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 bool g_profile = false;
 unsigned long long *g_phase = nullptr;
-cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
 int fail(int code, const char *fmt, const char *detail = "") {
     snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -229,7 +229,7 @@ int gfpp_last_launch_count(void) { return g_launches; }
 
 int gfpp_profile_enable(int on) {
     if (on && !g_ev[0]) {
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 5; ++i)
             if (cudaEventCreate(&g_ev[i]) != cudaSuccess) return fail(GFPP_ERR_CUDA, "cudaEventCreate failed%s");
     }
     g_profile = on != 0;
@@ -241,10 +241,11 @@ int gfpp_profile_phases(void *dev_u64x32) {
     return GFPP_OK;
 }
 
-int gfpp_profile_read(float ms[3]) {
+int gfpp_profile_read(float ms[4]) {
     if (!g_profile || !g_ev[0] || !ms) return fail(GFPP_ERR_INVALID, "profile_read: profiling is not enabled%s");
     CKN(cudaEventSynchronize(g_ev[3]));
     for (int i = 0; i < 3; ++i) CKN(cudaEventElapsedTime(&ms[i], g_ev[i], g_ev[i + 1]));
+    CKN(cudaEventElapsedTime(&ms[3], g_ev[4], g_ev[0]));   // everything before the head kernel: memset, torso biases, ray setup
     return GFPP_OK;
 }
 
@@ -540,6 +541,7 @@ int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfp
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)workspace;
     g_launches = 0;
+    if (g_profile) CKN(cudaEventRecord(g_ev[4], st));
     CKN(cudaMemsetAsync(ws + W.zero_begin, 0, W.zero_end - W.zero_begin, st));
 
     HeadArgs a;

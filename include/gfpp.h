@@ -188,7 +188,7 @@ GFPP_API int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fram
  * stream) around its three main kernels; gfpp_profile_read() waits for those events and returns the durations of the
  * most recent call in milliseconds: ms[0] = head pass 1, ms[1] = schedule + head pass 2, ms[2] = torso/composite epilogue. */
 GFPP_API int gfpp_profile_enable(int on);
-GFPP_API int gfpp_profile_read(float ms[3]);
+GFPP_API int gfpp_profile_read(float ms[4]);   /* ms[3] = everything before the head kernel (memset, torso biases, ray setup) */
 /* optional: device buffer of 32 uint64 that the tensor-core head kernel fills with per-phase cycle totals (thread 0 of each
  * CTA; slot 31 = batches processed); NULL switches it off.  Diagnostics only. */
 GFPP_API int gfpp_profile_phases(void *dev_u64x32);
