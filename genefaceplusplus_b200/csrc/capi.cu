@@ -25,6 +25,7 @@ cudaError_t launch_freq_encode(const float *, uint32_t, uint32_t, uint32_t, floa
 cudaError_t launch_occupancy_bounds(const uint8_t *, uint32_t, uint32_t, int *, cudaStream_t);
 cudaError_t launch_coarse_occupancy(const uint8_t *, uint32_t, uint32_t, uint32_t *, cudaStream_t);
 cudaError_t launch_pack_quads(const GridMeta &, const float *, float *, uint32_t, cudaStream_t);
+cudaError_t launch_pack_octs(const GridMeta &, const float *, void *, uint32_t, cudaStream_t);
 // tc_pack.cu
 cudaError_t launch_pack_tc_tile(const float *, int, int, int, int, int, int, int, int, unsigned char *, unsigned char *, cudaStream_t);
 cudaError_t launch_tc_selftest(const float *, int, const unsigned char *, const unsigned char *, int, int, int, int, float *, cudaStream_t);
@@ -105,6 +106,7 @@ struct ModelHost {
     GridMeta pos_gm, amb_gm, tor_gm;
     const float2 *pos_tab, *amb_tab, *tor_tab;
     const float4 *pos_quads, *amb_quads;
+    const uint4 *pos_octs, *amb_octs;
     const uint8_t *bitfield;
     const float *density_grid_torso;
     const float *torso_def0_src, *torso_can0_src, *torso_code;  // originals (per-frame bias fold reads them)
@@ -480,13 +482,26 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
         m.tc.w_hi = thi; m.tc.w_lo = tlo; m.tc.narrow_hi = nhi; m.tc.narrow_lo = nlo;
     }
 
+    // fp16 mode: fp16 "octs" (one 32-byte sector per sample-level; tables rounded to fp16 like the reference under
+    // autocast); every other mode: fp32 "quads" (bit-identical values).  Both occupy the same 32 bytes per entry.
+    const bool want_octs = want_quads && d->mlp_precision == 1 && getenv("GFPP_NO_OCTS") == nullptr;
     if (want_quads && m.pos_gm.quad_ok && m.pos_gm.dim == 3) {
-        CK(launch_pack_quads(m.pos_gm, d->position_grid.embeddings, (float *)(base + L.pos_quads), (uint32_t)pos_entries, st));
-        m.pos_quads = (const float4 *)(base + L.pos_quads);
+        if (want_octs) {
+            CK(launch_pack_octs(m.pos_gm, d->position_grid.embeddings, base + L.pos_quads, (uint32_t)pos_entries, st));
+            m.pos_octs = (const uint4 *)(base + L.pos_quads);
+        } else {
+            CK(launch_pack_quads(m.pos_gm, d->position_grid.embeddings, (float *)(base + L.pos_quads), (uint32_t)pos_entries, st));
+            m.pos_quads = (const float4 *)(base + L.pos_quads);
+        }
     }
     if (want_quads && m.amb_gm.quad_ok && m.amb_gm.dim == 3) {
-        CK(launch_pack_quads(m.amb_gm, d->ambient_grid.embeddings, (float *)(base + L.amb_quads), (uint32_t)amb_entries, st));
-        m.amb_quads = (const float4 *)(base + L.amb_quads);
+        if (want_octs) {
+            CK(launch_pack_octs(m.amb_gm, d->ambient_grid.embeddings, base + L.amb_quads, (uint32_t)amb_entries, st));
+            m.amb_octs = (const uint4 *)(base + L.amb_quads);
+        } else {
+            CK(launch_pack_quads(m.amb_gm, d->ambient_grid.embeddings, (float *)(base + L.amb_quads), (uint32_t)amb_entries, st));
+            m.amb_quads = (const float4 *)(base + L.amb_quads);
+        }
     }
 
     m.has_torso = d->has_torso;
@@ -549,6 +564,7 @@ int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfp
     a.pos_gm = m.pos_gm; a.amb_gm = m.amb_gm;
     a.pos_tab = m.pos_tab; a.amb_tab = m.amb_tab;
     a.pos_quads = m.pos_quads; a.amb_quads = m.amb_quads;
+    a.pos_octs = m.pos_octs; a.amb_octs = m.amb_octs;
     a.wide = m.wide; a.narrow = m.narrow;
     for (int c = 0; c < HEAD_NCHUNK; ++c) { a.chunk_off[c] = m.chunk_off[c]; a.chunk_k[c] = kChunkK[c]; }
     march_const_init(a.mc, m.bound, fr->dt_gamma, fr->max_steps, m.cascade, m.grid_size, m.bitfield);

@@ -14,6 +14,7 @@ struct HeadArgs {
     GridMeta pos_gm, amb_gm;
     const float2 *pos_tab, *amb_tab;
     const float4 *pos_quads, *amb_quads;   // sector-packed corner layout (nullptr: use the reference layout)
+    const uint4 *pos_octs, *amb_octs;      // fp16 oct layout (fp16 mode only; takes precedence over quads)
     const float *wide;              // concatenated k-major weight chunks, stream order
     int chunk_off[HEAD_NCHUNK];     // float offset of each chunk in `wide`
     int chunk_k[HEAD_NCHUNK];       // k-rows in each chunk (<= 72, multiple of 4)

@@ -149,11 +149,12 @@ __device__ __noinline__ void epilogue_wide(unsigned char *a_hi, unsigned char *a
 }
 
 // Four consecutive levels of a grid -> 8 features (one 16-byte operand chunk).  Out of line on purpose (I-cache).
-__device__ __noinline__ void lookup4(const GridMeta &gm, const float2 *__restrict__ table, const float4 *__restrict__ quads, int l0, float u,
-                                     float v, float w, float (&f)[8]) {
+__device__ __noinline__ void lookup4(const GridMeta &gm, const float2 *__restrict__ table, const float4 *__restrict__ quads,
+                                     const uint4 *__restrict__ octs, int l0, float u, float v, float w, float (&f)[8]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float2 g2 = (gm.dim == 3) ? (quads ? grid_lookup3q(gm, quads, l0 + j, u, v, w) : grid_lookup3(gm, table, l0 + j, u, v, w))
+        const float2 g2 = (gm.dim == 3) ? (octs ? grid_lookup3o(gm, octs, l0 + j, u, v, w)
+                                                : (quads ? grid_lookup3q(gm, quads, l0 + j, u, v, w) : grid_lookup3(gm, table, l0 + j, u, v, w)))
                                         : grid_lookup2(gm, table, l0 + j, u, v);
         f[2 * j] = g2.x;
         f[2 * j + 1] = g2.y;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {   // thread (slot, lg) owns levels lg*8 .. lg*8+7 = operand chunks 2lg, 2lg+1
                 float f[8];
-                if (v) lookup4(a.pos_gm, a.pos_tab, a.pos_quads, lg * 8 + c * 4, u, vv, w, f);
+                if (v) lookup4(a.pos_gm, a.pos_tab, a.pos_quads, a.pos_octs, lg * 8 + c * 4, u, vv, w, f);
                 else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) f[i] = 0.f;
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
                 tmem_ld8(tmem + (lane_base << 16) + TMEM_P + (uint32_t)(lg * 16 + c * 8), f);
                 wait_ld();
                 store_chunk<BF16, SPLIT>(s.a_hi[0], s.a_lo[0], sw128_off(slot, 2 * lg + c), f);
-                if (v) lookup4(a.amb_gm, a.amb_tab, a.amb_quads, lg * 8 + c * 4, u, vv, w, f);
+                if (v) lookup4(a.amb_gm, a.amb_tab, a.amb_quads, a.amb_octs, lg * 8 + c * 4, u, vv, w, f);
                 else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) f[i] = 0.f;

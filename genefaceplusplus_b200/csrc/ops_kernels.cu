@@ -198,7 +198,33 @@ __global__ void k_pack_quads(GridMeta gm, const float2 *__restrict__ table, floa
     }
 }
 
+// ---- fp16 oct layout of a tiled 3-D grid (common.cuh: grid_lookup3o) ----
+__global__ void k_pack_octs(GridMeta gm, const float2 *__restrict__ table, uint4 *__restrict__ octs, uint32_t total) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int l = 0;
+#pragma unroll 1
+        for (int k = 1; k < (int)gm.num_levels; ++k)
+            if (i >= gm.offset[k]) l = k;
+        const uint32_t q = i - gm.offset[l], m1 = gm.mul1[l], m2 = gm.mul2[l];
+        const float2 *tb = table + gm.offset[l];
+        uint32_t w[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float2 e = tb[grid_mod(gm, l, q + (c & 1) + ((c & 2) ? m1 : 0u) + ((c & 4) ? m2 : 0u))];
+            const __half2 h = __floats2half2_rn(e.x, e.y);
+            w[c] = *reinterpret_cast<const uint32_t *>(&h);
+        }
+        octs[2 * (size_t)i] = make_uint4(w[0], w[1], w[2], w[3]);
+        octs[2 * (size_t)i + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
+cudaError_t launch_pack_octs(const GridMeta &gm, const float *table, void *octs, uint32_t total, cudaStream_t st) {
+    k_pack_octs<<<grid_for(total, 256), 256, 0, st>>>(gm, (const float2 *)table, (uint4 *)octs, total);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pack_quads(const GridMeta &gm, const float *table, float *quads, uint32_t total, cudaStream_t st) {
     k_pack_quads<<<grid_for(total, 256), 256, 0, st>>>(gm, (const float2 *)table, (float4 *)quads, total);
     return cudaGetLastError();
