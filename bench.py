@@ -305,8 +305,12 @@ def main():
     alg_bytes = Fc * (S_per_frame * 2048 + N * (12 + 4 + 4)) + 0.36e6
     alg_flops = Fc * S_per_frame * 178944
     achieved = alg_bytes / head_t / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tp) and args.precision == "fp16":
+        traffic = json.load(open(tp))["dram_bytes_per_frame"] * Fc     # from one ncu --set full capture, scaled to this launch size
     roofline = {"bound": "hbm", "kernel": "k_head (pass 1)" if args.precision == "fp32" else "k_head_tc (pass 1)", "achieved": achieved, "peak": hbm, "peak_source": peak_kind, "unit": "GB/s",
-                "frac": achieved / hbm, "traffic": None, "launch_ms": head_t * 1000.0, "frames_per_launch": Fc,
+                "frac": achieved / hbm, "traffic": traffic, "launch_ms": head_t * 1000.0, "frames_per_launch": Fc,
                 "share_of_step": head_t / (head_t + (statistics.mean(pass2_ms) + statistics.mean(epi_ms) + statistics.mean(pre_ms)) / 1000),
                 "ray_setup_ms": statistics.mean(pre_ms),
                 "fp32_tflops": alg_flops / head_t / 1e12, "pass2_ms": statistics.mean(pass2_ms), "epilogue_ms": statistics.mean(epi_ms),
