@@ -156,7 +156,7 @@ def workload_name(args):
             f"max_steps=16, T_thresh=0.01, density_scale={args.density_scale:g}")
 
 
-def run_reference(args):
+def run_reference(args, out=sys.stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -176,13 +176,29 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"{args.cpu_frames} frame(s) at {args.size}x{args.size} per step, {args.steps} steps"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out)
+
+
+def _claim_stdout():
+    """Keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner to stdout) are redirected to stderr."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
 
 
 def main():
     args = parse()
+    out = _claim_stdout()
+    try:
+        return _main(args, out)
+    finally:
+        out.flush()
+
+
+def _main(args, out):
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
     import torch
     import torch.distributed as dist
     from genefaceplusplus_b200 import _capi, scene as scn
@@ -352,7 +368,7 @@ def main():
                 "clocks": clocks, "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                           "note": "pinned host poses+conditioning in, uint8 [T,H,W,3] frames out"},
                 "gpu_launches": timed_launches, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out)
     if world > 1:
         dist.destroy_process_group()
 
