@@ -613,10 +613,6 @@ int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfp
                                    (float *)(ws + W.bias_def), (float *)(ws + W.bias_can), st));
     }
 
-    {
-        const char *pb = getenv("GFPP_PARTNER_BUDGET");
-        a.partner_budget = pb ? atoi(pb) : 0;   // first-hit marching now lives in k_ray_setup; the in-kernel prefetcher is off
-    }
     a.phase_cycles = g_phase;
     a.pass = 1;
     a.cursor = counters + 0;

@@ -385,70 +385,6 @@ __device__ __forceinline__ float2 grid_lookup3o(const GridMeta &gm, const uint4 
     return acc;
 }
 
-// One x-half of the trilinear interpolation: the four (y,z) corners at x-cell gx + xbit, weighted.  The two lanes of a
-// pair (xbit 0/1) add their results.  Putting the two x-neighbours of a sample in ADJACENT LANES makes their 8-byte
-// entries (contiguous in the table) fall into one L1 wavefront: the gather is L1TEX-wavefront bound, and this halves the
-// wavefronts per sample (64 instead of 128 per table).
-__device__ __forceinline__ float2 grid_half3(const GridMeta &gm, const float2 *__restrict__ table, int l, float u, float v, float w,
-                                             int xbit) {
-    if (u < 0.f || u > 1.f || v < 0.f || v > 1.f || w < 0.f || w > 1.f) return make_float2(0.f, 0.f);
-    const float s = gm.scale[l];
-    float px = __fadd_rn(__fmul_rn(u, s), gm.align_off), py = __fadd_rn(__fmul_rn(v, s), gm.align_off),
-          pz = __fadd_rn(__fmul_rn(w, s), gm.align_off);
-    const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
-    const uint32_t gx = (uint32_t)fx0 + (uint32_t)xbit, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
-    px -= fx0; py -= fy0; pz -= fz0;
-    if (gm.interp == 1) {
-        px = px * px * (3.0f - 2.0f * px);
-        py = py * py * (3.0f - 2.0f * py);
-        pz = pz * pz * (3.0f - 2.0f * pz);
-    }
-    const float2 *tb = table + gm.offset[l];
-    float2 c[4];
-    if (!gm.hashed[l]) {
-        const uint32_t m1 = gm.mul1[l], m2 = gm.mul2[l], hm = gm.hmask[l], hs = gm.hsize[l];
-        const uint32_t base = gx + gy * m1 + gz * m2;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint32_t idx = base + ((i & 1) ? m1 : 0u) + ((i & 2) ? m2 : 0u);
-            if (hm) idx &= hm;
-            else if (idx >= hs) idx %= hs;
-            c[i] = __ldg(tb + idx);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) c[i] = __ldg(tb + grid_slot(gm, l, gx, gy + (i & 1), gz + ((i >> 1) & 1)));
-    }
-    const float wx = xbit ? px : 1.0f - px;
-    const float wy[2] = {1.0f - py, py}, wz[2] = {1.0f - pz, pz};
-    float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float wgt = wx * wy[i & 1] * wz[(i >> 1) & 1];
-        acc.x += wgt * c[i].x;
-        acc.y += wgt * c[i].y;
-    }
-    return acc;
-}
-
-__device__ __forceinline__ float2 grid_half2(const GridMeta &gm, const float2 *__restrict__ table, int l, float u, float v, int xbit) {
-    if (u < 0.f || u > 1.f || v < 0.f || v > 1.f) return make_float2(0.f, 0.f);
-    const float s = gm.scale[l];
-    float px = __fadd_rn(__fmul_rn(u, s), gm.align_off), py = __fadd_rn(__fmul_rn(v, s), gm.align_off);
-    const float fx0 = floorf(px), fy0 = floorf(py);
-    const uint32_t gx = (uint32_t)fx0 + (uint32_t)xbit, gy = (uint32_t)fy0;
-    px -= fx0; py -= fy0;
-    if (gm.interp == 1) {
-        px = px * px * (3.0f - 2.0f * px);
-        py = py * py * (3.0f - 2.0f * py);
-    }
-    const float2 *tb = table + gm.offset[l];
-    const float2 c0 = __ldg(tb + grid_slot(gm, l, gx, gy, 0u)), c1 = __ldg(tb + grid_slot(gm, l, gx, gy + 1, 0u));
-    const float wx = xbit ? px : 1.0f - px;
-    const float w0 = wx * (1.0f - py), w1 = wx * py;
-    return make_float2(w0 * c0.x + w1 * c1.x, w0 * c0.y + w1 * c1.y);
-}
-
 __device__ __forceinline__ float2 grid_lookup2(const GridMeta &gm, const float2 *__restrict__ table, int l, float u,
                                                float v) {
     if (u < 0.f || u > 1.f || v < 0.f || v > 1.f) return make_float2(0.f, 0.f);

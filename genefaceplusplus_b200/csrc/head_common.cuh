@@ -107,107 +107,13 @@ __device__ __forceinline__ bool setup_occupancy(const HeadArgs &a, MarchConst &m
     return have_box;
 }
 
-// one out-of-line copy of the marcher per kernel (three call sites; the kernels must stay I-cache friendly)
-// (results by value: reference parameters would force the marcher's loop state through local memory)
-struct MarchOut {
-    float t, x, y, z, dt;
-    int ok;
-};
-static __device__ __noinline__ MarchOut march_next_out(const MarchConst &mc, const RayGeom &g, float far, float t0) {
-    float t = t0, x = 0.f, y = 0.f, z = 0.f, dt = 0.f;
-    const bool ok = march_next(mc, g, far, t, x, y, z, dt);
-    MarchOut o;
-    o.t = t; o.x = x; o.y = y; o.z = z; o.dt = dt; o.ok = ok ? 1 : 0;
-    return o;
-}
-__device__ __forceinline__ bool march_next_nl(const MarchConst &mc, const RayGeom &g, float far, float &t, float &x, float &y, float &z,
-                                              float &dt) {
-#ifdef GFPP_OUTLINE_MARCH
-    const MarchOut o = march_next_out(mc, g, far, t);
-    t = o.t; x = o.x; y = o.y; z = o.z; dt = o.dt;
-    return o.ok != 0;
-#else
-    return march_next(mc, g, far, t, x, y, z, dt);
-#endif
-}
-
-// ---- partner prefetch --------------------------------------------------------------------------------------------
-// Threads TM..2*TM-1 own no ray slot and used to idle while the owners composite.  Thread TM+i is the PARTNER of slot i:
-// during the composite phase it fetches candidate rays from the CTA's work chunk and marches them (a bounded number of
-// cell steps per round, resumable) until one reaches its first occupied sample, then parks {ray id, t_pre} in
-// s.spare_*[i].  When slot i dies, its owner adopts the spare in O(1) instead of marching a new ray while the whole CTA
-// waits at a barrier.  s.spare_gid codes: >= 0 ready, -1 empty (partner idle), -2 partner busy (will deliver).
-struct Partner {
-    RayGeom g;
-    float far, far_m, t;
-    int gid;
-    int state;   // 0 idle, 1 marching
-};
-constexpr int kPartnerBudget = 24;   // cost units per round: 4 per fine-bitfield read, 1 per ALU-only cell step
-
-template <class SmemT>
-__device__ __forceinline__ void partner_step(const HeadArgs &a, SmemT &s, Partner &p, const MarchConst &mc, bool have_box,
-                                             const float (&occ_lo)[3], const float (&occ_hi)[3], int tid) {
-    constexpr int TM = HEAD_TM;
-    if (tid < TM || a.pass != 1 || a.partner_budget <= 0) return;
-    const int i = tid - TM;
-    int budget = a.partner_budget;
-    while (budget > 0) {
-        if (p.state == 0) {
-            if (s.spare_gid[i] != -1 || s.next >= s.end) break;      // spare still parked, or no work in the local chunk
-            const int w = atomicAdd(&s.next, 1);
-            if (w >= s.end) break;
-            budget -= 2;
-            p.gid = w;
-            const int frame = w / a.n_rays, ray = w - frame * a.n_rays;
-            load_ray(a, frame, ray, p.g);
-            float near;
-            near_far(p.g, a.aabb, a.min_near, near, p.far);
-            p.t = near;
-            if (!may_hit_occupied(have_box, occ_lo, occ_hi, p.g, near, p.far, p.far_m)) {
-                // no sample at all: the ray dies at position 1 (delta == 0): zeros out, depth normalised like the reference
-                Slot z;
-                z.g = p.g; z.near = near; z.far = p.far; z.gid = w; z.frame = frame;
-                z.ws = 0.f; z.depth = 0.f; z.r = z.gch = z.b = 0.f;
-                finalize_ray(a, z, true);
-                warp_agg_add(a.hist, frame * (a.max_steps + 2) + 1, 1);
-                continue;
-            }
-            p.state = 1;
-            s.spare_gid[i] = -2;
-        }
-        const int r = march_budget(mc, p.g, p.far_m, p.t, budget);
-        if (r == 2) break;                                            // out of budget: resume next round
-        if (r == 1) {                                                 // found: park it
-            s.spare_t[i] = p.t;
-            s.spare_gid[i] = p.gid;
-            p.state = 0;
-            break;
-        }
-        // exhausted without a sample
-        {
-            const int frame = p.gid / a.n_rays;
-            Slot z;
-            z.g = p.g; z.far = p.far; z.gid = p.gid; z.frame = frame;
-            float nr, fr;
-            near_far(p.g, a.aabb, a.min_near, nr, fr);
-            z.near = nr;
-            z.ws = 0.f; z.depth = 0.f; z.r = z.gch = z.b = 0.f;
-            finalize_ray(a, z, true);
-            warp_agg_add(a.hist, frame * (a.max_steps + 2) + 1, 1);
-        }
-        p.state = 0;
-        s.spare_gid[i] = -1;
-    }
-}
-
 constexpr int kFetchTries = 4;   // rays a thread may try per refill iteration (most candidates are cheap misses)
 constexpr int kRefillIters = 2;
 
 // Refill dead slots from the global work cursor, then publish the batch (valid flags, frame ids, sample positions).
 // Returns the number of valid rows, or -1 when the CTA is out of work.  All threads of the CTA must call it.
 template <class SmemT>
-__device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, Slot &sl, Partner &pt, const MarchConst &mc, bool have_box,
+__device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, Slot &sl, const MarchConst &mc, bool have_box,
                                                   const float (&occ_lo)[3], const float (&occ_hi)[3], int total, int tid) {
     constexpr int TM = HEAD_TM;
     for (int it = 0; it < kRefillIters; ++it) {
@@ -217,21 +123,7 @@ __device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, S
             else { s.next = base; s.end = min(base + TM, total); }
         }
         __syncthreads();
-        if (tid < TM && !sl.active && s.spare_gid[tid] >= 0) {
-            // adopt the ray the partner thread pre-marched: O(1), no marching on the critical path
-            const int gid = s.spare_gid[tid];
-            sl.gid = gid;
-            sl.frame = gid / a.n_rays;
-            load_ray(a, sl.frame, gid - sl.frame * a.n_rays, sl.g);
-            near_far(sl.g, a.aabb, a.min_near, sl.near, sl.far);
-            (void)may_hit_occupied(have_box, occ_lo, occ_hi, sl.g, sl.near, sl.far, sl.far_m);
-            sl.ws = 0.f; sl.depth = 0.f; sl.r = sl.gch = sl.b = 0.f;
-            sl.nsamp = 0; sl.cap = a.max_steps;
-            sample_at(mc, sl.g, s.spare_t[tid], sl.t, sl.px, sl.py, sl.pz, sl.dt);
-            sl.active = true;
-            s.spare_gid[tid] = -1;
-        }
-        if (tid < TM && !sl.active && s.spare_gid[tid] == -1) {       // -2: the partner is about to deliver, just wait
+        if (tid < TM && !sl.active) {
             for (int attempt = 0; attempt < kFetchTries && !sl.active && s.next < s.end; ++attempt) {
                 const int w = atomicAdd(&s.next, 1);
                 if (w >= s.end) break;
@@ -258,14 +150,14 @@ __device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, S
                     sl.r = a.image[3 * g]; sl.gch = a.image[3 * g + 1]; sl.b = a.image[3 * g + 2];
                     sl.nsamp = a.max_steps; sl.cap = a.B_total[sl.frame];
                     (void)may_hit_occupied(have_box, occ_lo, occ_hi, sl.g, sl.near, sl.far, sl.far_m);
-                    live = sl.nsamp < sl.cap && march_next_nl(mc, sl.g, sl.far_m, sl.t, sl.px, sl.py, sl.pz, sl.dt);
+                    live = sl.nsamp < sl.cap && march_next(mc, sl.g, sl.far_m, sl.t, sl.px, sl.py, sl.pz, sl.dt);
                     if (!live) finalize_ray(a, sl, true);
                 }
                 sl.active = live;
             }
         }
         // another iteration only pays off when slots are still empty AND the local chunk ran dry while work remains
-        const int want_more = __syncthreads_or(tid < TM && !sl.active && s.spare_gid[tid] == -1 && s.next >= s.end && !s.done);
+        const int want_more = __syncthreads_or(tid < TM && !sl.active && s.next >= s.end && !s.done);
         if (!want_more) break;
     }
     if (tid < TM) {
@@ -275,14 +167,9 @@ __device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, S
     }
     const int n_valid = __syncthreads_count(tid < TM && sl.active);
     if (n_valid == 0) {
-        // nothing to evaluate this round: finished only when the work is gone AND no partner still holds / marches a ray
-        const int pending = __syncthreads_count((tid < TM && s.spare_gid[tid] != -1) || (tid >= TM && pt.state != 0));
-        const bool out_of_work = s.done && s.next >= s.end && pending == 0;
+        const bool out_of_work = s.done && s.next >= s.end;
         __syncthreads();  // thread 0 must not start the next refill (which rewrites next/end/done) before everyone has read them
-        if (out_of_work) return -1;
-        partner_step(a, s, pt, mc, have_box, occ_lo, occ_hi, tid);   // keep the prefetchers moving
-        __syncthreads();  // ... and finished before thread 0 may hand out the next chunk (they read next/end)
-        return 0;
+        return out_of_work ? -1 : 0;
     }
     return n_valid;
 }
@@ -290,10 +177,8 @@ __device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, S
 // Front-to-back compositing of the batch's sample in the owner thread (raymarching.cu:978-1006), termination test,
 // then march to the ray's next sample (or retire the ray).
 template <class SmemT>
-__device__ __forceinline__ void composite_and_advance(const HeadArgs &a, SmemT &s, Slot &sl, Partner &pt, const MarchConst &mc,
-                                                      bool have_box, const float (&occ_lo)[3], const float (&occ_hi)[3], int tid) {
+__device__ __forceinline__ void composite_and_advance(const HeadArgs &a, SmemT &s, Slot &sl, const MarchConst &mc, int tid) {
     constexpr int TM = HEAD_TM;
-    partner_step(a, s, pt, mc, have_box, occ_lo, occ_hi, tid);
     if (tid < TM && sl.active) {
         const float sigma = s.sig[tid];
         const float alpha = 1.0f - expf(-sigma * sl.dt);
@@ -310,7 +195,7 @@ __device__ __forceinline__ void composite_and_advance(const HeadArgs &a, SmemT &
         bool suspend = false;
         if (T < a.T_thresh) D = sl.nsamp;
         else if (sl.nsamp >= sl.cap) suspend = true;
-        else if (!march_next_nl(mc, sl.g, sl.far_m, sl.t, sl.px, sl.py, sl.pz, sl.dt)) D = sl.nsamp + 1;
+        else if (!march_next(mc, sl.g, sl.far_m, sl.t, sl.px, sl.py, sl.pz, sl.dt)) D = sl.nsamp + 1;
         if (D) {
             finalize_ray(a, sl, true);
             if (a.pass == 1) warp_agg_add(a.hist, sl.frame * (a.max_steps + 2) + D, 1);

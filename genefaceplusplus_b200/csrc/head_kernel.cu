@@ -53,8 +53,6 @@ struct Smem {
     int valid[TM];
     unsigned long long bar[NSTAGE];
     uint32_t coarse[HEAD_COARSE_WORDS];
-    int spare_gid[HEAD_TM];   // partner prefetch hand-off (head_common.cuh)
-    float spare_t[HEAD_TM];
     int next, end, done;
 };
 
@@ -211,7 +209,6 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ Hea
     float occ_lo[3] = {0.f, 0.f, 0.f}, occ_hi[3] = {0.f, 0.f, 0.f};
     const bool have_box = setup_occupancy(a, mc, occ_lo, occ_hi);
     install_coarse(a, s, mc, tid, NT);
-    if (tid < TM) s.spare_gid[tid] = -1;
     for (int i = tid; i < 8 * 128; i += NT) s.narrow[i] = a.narrow[i];
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) mbar_init(&s.bar[i], 1);
@@ -228,12 +225,10 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ Hea
     Slot sl;
     sl.active = false;
     sl.gid = 0; sl.frame = 0; sl.nsamp = 0; sl.cap = 0;
-    Partner pt;
-    pt.state = 0; pt.gid = 0; pt.t = 0.f; pt.far = 0.f;
 
     for (;;) {
         // ================= refill dead slots from the global cursor, publish the batch (head_common.cuh) =================
-        const int n_valid = refill_and_publish(a, s, sl, pt, mc, have_box, occ_lo, occ_hi, total, tid);
+        const int n_valid = refill_and_publish(a, s, sl, mc, have_box, occ_lo, occ_hi, total, tid);
         if (n_valid < 0) break;
         if (n_valid == 0) continue;
 
@@ -368,7 +363,7 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head(const __grid_constant__ Hea
         __syncthreads();
 
         // ================= composite + advance (head_common.cuh) =================
-        composite_and_advance(a, s, sl, pt, mc, have_box, occ_lo, occ_hi, tid);
+        composite_and_advance(a, s, sl, mc, tid);
         // no barrier needed here: the refill starts with one before shared memory is touched again
     }
 

@@ -50,7 +50,6 @@ struct HeadArgs {
     int *valid_samples;             // [F] statistics (or nullptr)
     int pass;                       // 1 or 2
     unsigned long long *phase_cycles;  // optional [32]: per-phase cycle totals of thread 0 of every CTA (diagnostics)
-    int partner_budget;             // per-round prefetch budget of the partner threads (0 = prefetch off)
 };
 
 // tensor-core variant: pre-swizzled 16-bit weight tiles (see pack_tc_weights in capi.cu)

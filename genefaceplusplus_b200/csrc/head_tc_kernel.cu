@@ -61,8 +61,6 @@ struct SmemTC {
     unsigned long long bar_acc;
     uint32_t tmem_base;
     uint32_t coarse[HEAD_COARSE_WORDS];
-    int spare_gid[HEAD_TM];   // partner prefetch hand-off (head_common.cuh)
-    float spare_t[HEAD_TM];
     int next, end, done;
 };
 
@@ -175,7 +173,6 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
     float occ_lo[3] = {0.f, 0.f, 0.f}, occ_hi[3] = {0.f, 0.f, 0.f};
     const bool have_box = setup_occupancy(a, mc, occ_lo, occ_hi);
     install_coarse(a, s, mc, tid, NT);
-    if (tid < TM) s.spare_gid[tid] = -1;
     if (warp == 0) tmem_alloc(&s.tmem_base, TMEM_COLS);
     if (tid == 32) {
         for (int i = 0; i < W_NSTAGE; ++i) mbar_init(&s.bar_full[i], 1);
@@ -205,8 +202,6 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
     Slot sl;
     sl.active = false;
     sl.gid = 0; sl.frame = 0; sl.nsamp = 0; sl.cap = 0;
-    Partner pt;
-    pt.state = 0; pt.gid = 0; pt.t = 0.f; pt.far = 0.f;
 
     long long ph_last = clock64();
 #define PH(i)                                                                                   \
@@ -217,7 +212,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
     }
     for (;;) {
         // ================= refill dead slots from the global cursor, publish the batch (head_common.cuh) =================
-        const int n_valid = refill_and_publish(a, s, sl, pt, mc, have_box, occ_lo, occ_hi, total, tid);
+        const int n_valid = refill_and_publish(a, s, sl, mc, have_box, occ_lo, occ_hi, total, tid);
         if (n_valid < 0) break;
         if (n_valid == 0) continue;
         PH(0)   // refill + publish
@@ -368,7 +363,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
 
         PH(9)   // color net: 2 MMA layers + epilogue + sigmoid
         // ================= composite + advance (head_common.cuh) =================
-        composite_and_advance(a, s, sl, pt, mc, have_box, occ_lo, occ_hi, tid);
+        composite_and_advance(a, s, sl, mc, tid);
         PH(10)  // composite + march to next sample
         if (a.phase_cycles && tid == 0) atomicAdd(a.phase_cycles + 31, 1ull);   // batches
         // no barrier needed here: the refill starts with one before shared memory is touched again
