@@ -44,13 +44,13 @@ struct SmemTC {
     // SW128 tiles must start on 1024-byte boundaries (the swizzle is a function of the shared-memory address bits)
     alignas(1024) unsigned char a_hi[2][A_TILE];
     alignas(1024) unsigned char w_hi[W_NSTAGE][W_HALF];
-    alignas(1024) unsigned char n_hi[4][2048];   // resident narrow weights: ambient-out k-tiles 0,1; color-out k-tiles 0,1 ([16 x 64] SW128)
     alignas(SPLIT ? 1024 : 16) unsigned char a_lo[SPLIT ? 2 : 1][SPLIT ? A_TILE : 16];
     alignas(SPLIT ? 1024 : 16) unsigned char w_lo[SPLIT ? W_NSTAGE : 1][SPLIT ? W_HALF : 16];
-    alignas(SPLIT ? 1024 : 16) unsigned char n_lo[SPLIT ? 4 : 1][SPLIT ? 2048 : 16];
     alignas(256) unsigned char s_hi[A_K16];
     alignas(SPLIT ? 256 : 16) unsigned char s_lo[SPLIT ? A_K16 : 16];
     float bias[128];                  // color L0 bias (individual code folded)
+    float nw[6 * 128];                // fp32 rows of the two 3-wide output layers: ambient out (0-2), color out (3-5)
+    float part[2 * 3 * TM];           // their partial dot products, one per column half
     float sx[TM], sy[TM], sz[TM];
     float amb[3 * TM];
     float sig[TM];
@@ -95,16 +95,6 @@ __device__ __forceinline__ void issue_layer(const HeadTcArgs &t, SmemTC<SPLIT> &
     mma_commit(&s.bar_acc);
 }
 
-// Thread 0: a narrow (N=16) layer from the resident weights, K = 128 (two SW128 k-tiles)
-template <bool SPLIT>
-__device__ __forceinline__ void issue_narrow(SmemTC<SPLIT> &s, int which, uint32_t d_tmem, uint32_t idesc16) {
-    fence_after_sync();
-    for (int c = 0; c < 2; ++c)
-        issue_ktile(d_tmem, smem_u32(s.a_hi[c]), smem_u32(s.a_lo[SPLIT ? c : 0]), smem_u32(s.n_hi[which * 2 + c]),
-                    smem_u32(s.n_lo[SPLIT ? which * 2 + c : 0]), 4, false, SPLIT, idesc16, c > 0);
-    mma_commit(&s.bar_acc);
-}
-
 // All threads: wait for the accumulator; thread 0 then refills the weight stages the layer has released.
 template <bool SPLIT>
 __device__ __forceinline__ void wait_acc(const HeadTcArgs &t, SmemTC<SPLIT> &s, Stream &st, int nchunks, int tid) {
@@ -116,15 +106,20 @@ __device__ __forceinline__ void wait_acc(const HeadTcArgs &t, SmemTC<SPLIT> &s, 
     st.consumed += nchunks;
 }
 
-// Epilogue of a 128-wide layer: thread (row, half) reads 64 accumulator columns (two passes of 32), applies bias/ReLU
-// and writes them as the next layer's A operand (k = column) into tile `half`.  Not inlined: it is called six times per
-// batch and the kernel must stay instruction-cache friendly.
-template <bool BF16, bool SPLIT, bool RELU, bool BIAS>
-__device__ __noinline__ void epilogue_wide(unsigned char *a_hi, unsigned char *a_lo, uint32_t tmem, int tid, const float *bias) {
+// Epilogue of a 128-wide layer: thread (row, half) reads 64 accumulator columns (two passes of 32), applies bias/ReLU and
+//   * NARROW == false: writes them as the next layer's A operand (k = column) into tile `half`;
+//   * NARROW == true : the layer feeds only a 3-wide output layer (ambient coordinates / rgb), so the activations never go
+//     back to shared memory: the thread accumulates its half of the three dot products in fp32 (weights `nw`, [3][128])
+//     and stores the partials in part[half][o][row] -- no fp16 round trip, no extra MMA, no extra barrier.
+// Not inlined: it is called six times per batch and the kernel must stay instruction-cache friendly.
+template <bool BF16, bool SPLIT, bool RELU, bool BIAS, bool NARROW>
+__device__ __noinline__ void epilogue_wide(unsigned char *a_hi, unsigned char *a_lo, uint32_t tmem, int tid, const float *bias,
+                                           const float *nw, float *part) {
     const int row = tid & 127, half = tid >> 7;
     const uint32_t lane_base = (uint32_t)((tid >> 5) & 3) * 32u;
     const uint32_t taddr = tmem + (lane_base << 16) + (uint32_t)half * 64u;
     unsigned char *hi = a_hi + half * A_TILE, *lo = a_lo + (SPLIT ? half * A_TILE : 0);
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll 1
     for (int p = 0; p < 2; ++p) {
         float v[2][16];
@@ -135,14 +130,27 @@ __device__ __noinline__ void epilogue_wide(unsigned char *a_hi, unsigned char *a
         for (int q = 0; q < 2; ++q) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
+                const int col = half * 64 + p * 32 + q * 16 + i;
                 float x = v[q][i];
-                if (BIAS) x += bias[half * 64 + p * 32 + q * 16 + i];
+                if (BIAS) x += bias[col];
                 if (RELU) x = fmaxf(x, 0.f);
                 v[q][i] = x;
+                if (NARROW) {
+                    d0 = fmaf(x, nw[col], d0);
+                    d1 = fmaf(x, nw[128 + col], d1);
+                    d2 = fmaf(x, nw[256 + col], d2);
+                }
             }
-            store_chunk<BF16, SPLIT>(hi, lo, sw128_off(row, 4 * p + 2 * q), &v[q][0]);
-            store_chunk<BF16, SPLIT>(hi, lo, sw128_off(row, 4 * p + 2 * q + 1), &v[q][8]);
+            if (!NARROW) {
+                store_chunk<BF16, SPLIT>(hi, lo, sw128_off(row, 4 * p + 2 * q), &v[q][0]);
+                store_chunk<BF16, SPLIT>(hi, lo, sw128_off(row, 4 * p + 2 * q + 1), &v[q][8]);
+            }
         }
+    }
+    if (NARROW) {
+        part[(half * 3 + 0) * TM + row] = d0;
+        part[(half * 3 + 1) * TM + row] = d1;
+        part[(half * 3 + 2) * TM + row] = d2;
     }
 }
 
@@ -180,9 +188,9 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
         mbar_fence_init();
         s.next = 0; s.end = 0; s.done = 0;
     }
-    for (int i = tid; i < 4 * 2048 / 16; i += NT) {
-        reinterpret_cast<uint4 *>(&s.n_hi[0][0])[i] = reinterpret_cast<const uint4 *>(t.narrow_hi)[i];
-        if (SPLIT) reinterpret_cast<uint4 *>(&s.n_lo[0][0])[i] = reinterpret_cast<const uint4 *>(t.narrow_lo)[i];
+    for (int i = tid; i < 3 * 128; i += NT) {   // a.narrow rows: 0-2 ambient out, 3 sigma, 4-6 color out, 7 color-L0 bias
+        s.nw[i] = a.narrow[i];
+        s.nw[3 * 128 + i] = a.narrow[4 * 128 + i];
     }
     if (tid < 128) s.bias[tid] = a.narrow[7 * 128 + tid];
     fence_async_smem();
@@ -195,7 +203,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
     Stream st;
     st.consumed = 0;
     st.acc_uses = 0;
-    const uint32_t idesc128 = make_idesc(BF16 ? 1 : 0, 128), idesc144 = make_idesc(BF16 ? 1 : 0, 144), idesc16 = make_idesc(BF16 ? 1 : 0, 16);
+    const uint32_t idesc128 = make_idesc(BF16 ? 1 : 0, 128), idesc144 = make_idesc(BF16 ? 1 : 0, 144);
     const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
 
     const int total = (a.pass == 1) ? *a.n_hits : *a.n_survivors;
@@ -264,28 +272,24 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
         if (tid == 0) issue_layer<SPLIT>(t, s, st, 2, tmem, idesc128);
         wait_acc<SPLIT>(t, s, st, 2, tid);
         PH(2)   // MMA issue + wait (ambient L0)
-        epilogue_wide<BF16, SPLIT, true, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr);
+        epilogue_wide<BF16, SPLIT, true, false, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr, nullptr, nullptr);
         fence_async_smem(); fence_before_sync(); __syncthreads();
         PH(3)   // epilogue (ambient L0) + barrier
         if (tid == 0) issue_layer<SPLIT>(t, s, st, 2, tmem, idesc128);
         wait_acc<SPLIT>(t, s, st, 2, tid);
         PH(4)   // MMA (ambient L1)
-        epilogue_wide<BF16, SPLIT, true, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr);
-        fence_async_smem(); fence_before_sync(); __syncthreads();
-        PH(5)   // epilogue (ambient L1)
-        if (tid == 0) issue_narrow<SPLIT>(s, 0, tmem, idesc16);
-        wait_acc<SPLIT>(t, s, st, 0, tid);
-        if (tid < TM) {
-            float o[16];
-            tmem_ld16(tmem + (lane_base << 16), o);
-            wait_ld();
-            s.amb[tid] = tanhf(o[0]);
-            s.amb[TM + tid] = tanhf(o[1]);
-            s.amb[2 * TM + tid] = tanhf(o[2]);
-        }
+        // ambient L1 epilogue fused with the 3-wide ambient output layer (fp32 dot products straight from the accumulators)
+        epilogue_wide<BF16, SPLIT, true, false, true>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr, s.nw, s.part);
         fence_before_sync();
         __syncthreads();
         fence_after_sync();
+        PH(5)   // epilogue (ambient L1) + partial dots
+        if (tid < TM) {
+            s.amb[tid] = tanhf(s.part[0 * TM + tid] + s.part[3 * TM + tid]);
+            s.amb[TM + tid] = tanhf(s.part[1 * TM + tid] + s.part[4 * TM + tid]);
+            s.amb[2 * TM + tid] = tanhf(s.part[2 * TM + tid] + s.part[5 * TM + tid]);
+        }
+        __syncthreads();
         PH(6)   // narrow ambient out: MMA + tanh
         // ---- sigma-net input: tile0 k[0,32) <- parked position features, k[32,64) <- ambient grid ----
         {
@@ -315,11 +319,11 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
         // ---- sigma net 64 -> 128 -> 128 -> (128 geo + sigma) ----
         if (tid == 0) issue_layer<SPLIT>(t, s, st, 1, tmem, idesc128);
         wait_acc<SPLIT>(t, s, st, 1, tid);
-        epilogue_wide<BF16, SPLIT, true, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr);
+        epilogue_wide<BF16, SPLIT, true, false, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr, nullptr, nullptr);
         fence_async_smem(); fence_before_sync(); __syncthreads();
         if (tid == 0) issue_layer<SPLIT>(t, s, st, 2, tmem, idesc128);
         wait_acc<SPLIT>(t, s, st, 2, tid);
-        epilogue_wide<BF16, SPLIT, true, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr);
+        epilogue_wide<BF16, SPLIT, true, false, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr, nullptr, nullptr);
         fence_async_smem(); fence_before_sync(); __syncthreads();
         if (tid == 0) issue_layer<SPLIT>(t, s, st, 2, tmem, idesc144);
         wait_acc<SPLIT>(t, s, st, 2, tid);
@@ -338,28 +342,24 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
             store_chunk<BF16, SPLIT>(s.s_hi, s.s_lo, k16_off(tid, 0), &sh[0]);
             store_chunk<BF16, SPLIT>(s.s_hi, s.s_lo, k16_off(tid, 1), &sh[8]);
         }
-        epilogue_wide<BF16, SPLIT, false, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr);   // geo features -> tiles 0,1 (k = 0..127)
+        epilogue_wide<BF16, SPLIT, false, false, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr, nullptr, nullptr);   // geo features -> tiles 0,1 (k = 0..127)
         fence_async_smem(); fence_before_sync(); __syncthreads();
 
         PH(8)   // sigma net: 3 MMA layers + 3 epilogues
         // ---- color net (128 geo + 16 SH [+ folded individual code]) -> 128 -> 3 ----
         if (tid == 0) issue_layer<SPLIT>(t, s, st, 3, tmem, idesc128);
         wait_acc<SPLIT>(t, s, st, 3, tid);
-        epilogue_wide<BF16, SPLIT, true, true>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, s.bias);
-        fence_async_smem(); fence_before_sync(); __syncthreads();
-        if (tid == 0) issue_narrow<SPLIT>(s, 1, tmem, idesc16);
-        wait_acc<SPLIT>(t, s, st, 0, tid);
-        if (tid < TM) {
-            float o[16];
-            tmem_ld16(tmem + (lane_base << 16), o);
-            wait_ld();
-            s.rgb[tid] = 1.0f / (1.0f + expf(-o[0]));
-            s.rgb[TM + tid] = 1.0f / (1.0f + expf(-o[1]));
-            s.rgb[2 * TM + tid] = 1.0f / (1.0f + expf(-o[2]));
-        }
+        // color L0 epilogue fused with the 3-wide rgb output layer
+        epilogue_wide<BF16, SPLIT, true, true, true>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, s.bias, s.nw + 3 * 128, s.part);
         fence_before_sync();
         __syncthreads();
         fence_after_sync();
+        if (tid < TM) {
+            s.rgb[tid] = 1.0f / (1.0f + expf(-(s.part[0 * TM + tid] + s.part[3 * TM + tid])));
+            s.rgb[TM + tid] = 1.0f / (1.0f + expf(-(s.part[1 * TM + tid] + s.part[4 * TM + tid])));
+            s.rgb[2 * TM + tid] = 1.0f / (1.0f + expf(-(s.part[2 * TM + tid] + s.part[5 * TM + tid])));
+        }
+        __syncthreads();
 
         PH(9)   // color net: 2 MMA layers + epilogue + sigmoid
         // ================= composite + advance (head_common.cuh) =================
