@@ -132,16 +132,9 @@ struct PackedLayout {
     size_t wide, narrow, wd0, wd1, wd2, wc0, wc1, wc2, occ, coarse, tc_hi, tc_lo, tcn_hi, tcn_lo, pos_quads, amb_quads, total;
 };
 
-// tensor-core weight stream: 12 tiles per batch (see head_tc_kernel.cu)
-struct TcChunk { int layer, rows, col0, kc, k16; };
-constexpr TcChunk kTc[HEAD_TC_NCHUNK] = {
-    {0, 128, 0, 64, 0}, {0, 128, 64, 32, 0},     // ambient L0 (K = 96)
-    {1, 128, 0, 64, 0}, {1, 128, 64, 64, 0},     // ambient L1
-    {2, 128, 0, 64, 0},                          // sigma L0 (K = 64)
-    {3, 128, 0, 64, 0}, {3, 128, 64, 64, 0},     // sigma L1
-    {4, 144, 0, 64, 0}, {4, 144, 64, 64, 0},     // sigma L2: rows 0..127 geo, row 128 sigma, rest zero
-    {5, 128, 16, 64, 0}, {5, 128, 80, 64, 0},    // color L0, geo columns 16..143
-    {5, 128, 0, 16, 1}};                         // color L0, SH columns 0..15 (K16 tile)
+// tensor-core weight stream: kHeadTcChunks (head_kernel.cuh)
+using TcChunk = HeadTcChunk;
+constexpr const HeadTcChunk *kTc = kHeadTcChunks;
 inline int tc_chunk_bytes(int c) { return kTc[c].rows * (kTc[c].k16 ? 32 : 128); }
 
 inline size_t coarse_words_for(uint32_t cascade, uint32_t grid_size) {

@@ -315,6 +315,14 @@ __device__ __forceinline__ uint32_t grid_mod(const GridMeta &gm, int l, uint32_t
     return idx >= hs ? idx % hs : idx;
 }
 
+// one 256-bit read-only global load (sm_100: LDG.E.256); p must be 32-byte aligned.  (The .v4.u64 form: ptxas 12.9 crashes on
+// .v8.u32 in this translation unit.)
+__device__ __forceinline__ void ldg256(const uint4 *p, uint4 &lo, uint4 &hi) {
+    unsigned long long a, b, c2, d;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c2), "=l"(d) : "l"(p));
+    lo.x = (uint32_t)a; lo.y = (uint32_t)(a >> 32); lo.z = (uint32_t)b; lo.w = (uint32_t)(b >> 32);
+    hi.x = (uint32_t)c2; hi.y = (uint32_t)(c2 >> 32); hi.z = (uint32_t)d; hi.w = (uint32_t)(d >> 32);
+}
 __device__ __forceinline__ float2 grid_lookup3q(const GridMeta &gm, const float4 *__restrict__ quads, int l, float u, float v, float w) {
     if (u < 0.f || u > 1.f || v < 0.f || v > 1.f || w < 0.f || w > 1.f) return make_float2(0.f, 0.f);
     const float s = gm.scale[l];
@@ -334,7 +342,11 @@ __device__ __forceinline__ float2 grid_lookup3q(const GridMeta &gm, const float4
     // (levels whose z stride was dropped -- m2 == 0, get_grid_index quirk H5 -- read the same block twice: an L1 hit; a
     //  branch to skip it measured slower)
     const uint32_t q0 = grid_mod(gm, l, base), q1 = grid_mod(gm, l, base + m2);
-    const float4 a0 = __ldg(qb + 2 * q0), a1 = __ldg(qb + 2 * q0 + 1), b0 = __ldg(qb + 2 * q1), b1 = __ldg(qb + 2 * q1 + 1);
+    uint4 ua0, ua1, ub0, ub1;
+    ldg256(reinterpret_cast<const uint4 *>(qb + 2 * q0), ua0, ua1);
+    ldg256(reinterpret_cast<const uint4 *>(qb + 2 * q1), ub0, ub1);
+    const float4 a0 = *reinterpret_cast<float4 *>(&ua0), a1 = *reinterpret_cast<float4 *>(&ua1),
+                 b0 = *reinterpret_cast<float4 *>(&ub0), b1 = *reinterpret_cast<float4 *>(&ub1);
     // same corner order and factor order as grid_lookup3: i = dx + 2 dy + 4 dz,  w = (x term) * (y term) * (z term)
     const float wx0 = 1.0f - px, wy0 = 1.0f - py, wz0 = 1.0f - pz;
     float2 acc = make_float2(0.f, 0.f);
@@ -370,8 +382,8 @@ __device__ __forceinline__ float2 grid_lookup3o(const GridMeta &gm, const uint4 
         pz = pz * pz * (3.0f - 2.0f * pz);
     }
     const uint32_t q = grid_mod(gm, l, gx + gy * gm.mul1[l] + gz * gm.mul2[l]);
-    const uint4 *ob = octs + 2 * ((size_t)gm.offset[l] + q);
-    const uint4 lo4 = __ldg(ob), hi4 = __ldg(ob + 1);
+    uint4 lo4, hi4;
+    ldg256(octs + 2 * ((size_t)gm.offset[l] + q), lo4, hi4);
     const uint32_t c[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
     const float wx[2] = {1.0f - px, px}, wy[2] = {1.0f - py, py}, wz[2] = {1.0f - pz, pz};
     float2 acc = make_float2(0.f, 0.f);

@@ -54,6 +54,21 @@ struct HeadArgs {
 
 // tensor-core variant: pre-swizzled 16-bit weight tiles (see pack_tc_weights in capi.cu)
 constexpr int HEAD_TC_NCHUNK = 12;
+// The weight stream of one batch: 12 tiles, always in this order (the kernel's schedule is compiled against this table,
+// gfpp_model_pack fills the tiles from it).  rows x kc slice of layer `layer` starting at input column col0; k16 marks the
+// no-swizzle K = 16 tile that pairs with the SH operand tile.
+struct HeadTcChunk { int layer, rows, col0, kc, k16; };
+constexpr HeadTcChunk kHeadTcChunks[HEAD_TC_NCHUNK] = {
+    {0, 128, 0, 64, 0}, {0, 128, 64, 32, 0},     // ambient L0 (K = 96)
+    {1, 128, 0, 64, 0}, {1, 128, 64, 64, 0},     // ambient L1
+    {2, 128, 0, 64, 0},                          // sigma L0 (K = 64)
+    {3, 128, 0, 64, 0}, {3, 128, 64, 64, 0},     // sigma L1
+    {4, 144, 0, 64, 0}, {4, 144, 64, 64, 0},     // sigma L2: rows 0..127 geo, row 128 sigma, rest zero
+    {5, 128, 16, 64, 0}, {5, 128, 80, 64, 0},    // color L0, geo columns 16..143
+    {5, 128, 0, 16, 1}};                         // color L0, SH columns 0..15 (K16 tile)
+constexpr int head_tc_chunk_bytes(int c) { return kHeadTcChunks[c].rows * (kHeadTcChunks[c].k16 ? 32 : 128); }
+constexpr int head_tc_chunk_off(int c) { return c == 0 ? 0 : head_tc_chunk_off(c - 1) + head_tc_chunk_bytes(c - 1); }
+constexpr int head_tc_chunk_ksteps(int c) { return kHeadTcChunks[c].k16 ? 1 : kHeadTcChunks[c].kc / 16; }
 struct HeadTcArgs {
     const unsigned char *w_hi, *w_lo;       // streamed tiles, hi and lo images with identical layout
     int chunk_off[HEAD_TC_NCHUNK];          // byte offset of each tile

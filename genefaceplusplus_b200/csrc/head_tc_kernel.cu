@@ -64,46 +64,84 @@ struct SmemTC {
     int next, end, done;
 };
 
-struct Stream {
-    uint32_t consumed;   // weight chunks consumed so far (uniform across the CTA)
-    uint32_t acc_uses;   // completed accumulator hand-offs
-};
+// The weight stream is static: batch b consumes tiles b*12 + (0..11) in the order of kHeadTcChunks, and 12 is a multiple
+// of the ring depth, so tile id c always lives in stage c % W_NSTAGE and completes the mbarrier phase (c / W_NSTAGE) & 1.
+// Everything the issuing warp needs is therefore a compile-time constant or a CTA-uniform address: the MMA / bulk-copy
+// operands sit in uniform registers and one elected lane of warp 0 issues them back to back.  (A lone `tid == 0` branch
+// makes the compiler wrap every tcgen05.mma in a register->uniform-register waterfall loop: ~250 cycles per MMA.)
+static_assert(HEAD_TC_NCHUNK % W_NSTAGE == 0, "the static stage/parity schedule needs the ring depth to divide the tiles per batch");
 
-template <bool SPLIT>
-__device__ __forceinline__ void issue_load(const HeadTcArgs &t, SmemTC<SPLIT> &s, uint32_t seq) {
-    const uint32_t stage = seq % W_NSTAGE, id = seq % HEAD_TC_NCHUNK;
-    const uint32_t bytes = (uint32_t)t.chunk_bytes[id];
+template <bool SPLIT, int ID>
+__device__ __forceinline__ void issue_load(const HeadTcArgs &t, SmemTC<SPLIT> &s) {
+    constexpr int id = ID % HEAD_TC_NCHUNK, stage = id % W_NSTAGE;
+    constexpr uint32_t bytes = (uint32_t)head_tc_chunk_bytes(id), off = (uint32_t)head_tc_chunk_off(id);
     mbar_expect_tx(&s.bar_full[stage], SPLIT ? 2 * bytes : bytes);
-    bulk_g2s(s.w_hi[stage], t.w_hi + t.chunk_off[id], bytes, &s.bar_full[stage]);
-    if (SPLIT) bulk_g2s(s.w_lo[SPLIT ? stage : 0], t.w_lo + t.chunk_off[id], bytes, &s.bar_full[stage]);
+    bulk_g2s(s.w_hi[stage], t.w_hi + off, bytes, &s.bar_full[stage]);
+    if (SPLIT) bulk_g2s(s.w_lo[SPLIT ? stage : 0], t.w_lo + off, bytes, &s.bar_full[stage]);
 }
-
-// Thread 0: issue one layer = `nchunks` streamed weight tiles against A tiles 0,1 (and the K16 SH tile for a k16 chunk).
-template <bool SPLIT>
-__device__ __forceinline__ void issue_layer(const HeadTcArgs &t, SmemTC<SPLIT> &s, Stream &st, int nchunks, uint32_t d_tmem, uint32_t idesc) {
-    fence_after_sync();
-    uint32_t seq = st.consumed;
-    for (int c = 0; c < nchunks; ++c, ++seq) {
-        const uint32_t stage = seq % W_NSTAGE, id = seq % HEAD_TC_NCHUNK;
-        mbar_wait(&s.bar_full[stage], (seq / W_NSTAGE) & 1);
-        fence_after_sync();
-        const bool k16 = t.chunk_k16[id] != 0;
-        const uint32_t ah = k16 ? smem_u32(s.s_hi) : smem_u32(s.a_hi[c]);
-        const uint32_t al = k16 ? smem_u32(s.s_lo) : smem_u32(s.a_lo[SPLIT ? c : 0]);
-        issue_ktile(d_tmem, ah, al, smem_u32(s.w_hi[stage]), smem_u32(s.w_lo[SPLIT ? stage : 0]), t.chunk_ksteps[id], k16, SPLIT, idesc, c > 0);
+template <bool SPLIT, int ID, int N>
+__device__ __forceinline__ void issue_loads(const HeadTcArgs &t, SmemTC<SPLIT> &s) {
+    if constexpr (N > 0) {
+        issue_load<SPLIT, ID>(t, s);
+        issue_loads<SPLIT, ID + 1, N - 1>(t, s);
     }
-    mma_commit(&s.bar_acc);
 }
 
-// All threads: wait for the accumulator; thread 0 then refills the weight stages the layer has released.
-template <bool SPLIT>
-__device__ __forceinline__ void wait_acc(const HeadTcArgs &t, SmemTC<SPLIT> &s, Stream &st, int nchunks, int tid) {
-    mbar_wait(&s.bar_acc, st.acc_uses & 1);
-    st.acc_uses += 1;
+template <bool SPLIT, int ID, bool ACC0>
+__device__ __forceinline__ void issue_tile_mmas(SmemTC<SPLIT> &s, int a_tile, uint32_t d_tmem, uint32_t idesc) {
+    constexpr int stage = ID % W_NSTAGE, ksteps = head_tc_chunk_ksteps(ID);
+    constexpr bool k16 = kHeadTcChunks[ID].k16 != 0;
+    const uint32_t ah = k16 ? smem_u32(s.s_hi) : smem_u32(s.a_hi[a_tile]);
+    const uint32_t al = k16 ? smem_u32(s.s_lo) : smem_u32(s.a_lo[SPLIT ? a_tile : 0]);
+    const uint32_t wh = smem_u32(s.w_hi[stage]), wl = smem_u32(s.w_lo[SPLIT ? stage : 0]);
+#pragma unroll
+    for (int k = 0; k < ksteps; ++k) {
+        const uint32_t adv = (uint32_t)k * 32u;   // 16 elements x 2 B inside the 128-byte swizzle row
+        const uint64_t dah = k16 ? desc_k16(ah) : desc_sw128(ah + adv), dwh = k16 ? desc_k16(wh) : desc_sw128(wh + adv);
+        if (SPLIT) {
+            const uint64_t dal = k16 ? desc_k16(al) : desc_sw128(al + adv), dwl = k16 ? desc_k16(wl) : desc_sw128(wl + adv);
+            if (ACC0 || k > 0) mma_f16_s<true>(d_tmem, dal, dwh, idesc);   // small terms first
+            else mma_f16_s<false>(d_tmem, dal, dwh, idesc);
+            mma_f16_s<true>(d_tmem, dah, dwl, idesc);
+            mma_f16_s<true>(d_tmem, dah, dwh, idesc);
+        } else {
+            if (ACC0 || k > 0) mma_f16_s<true>(d_tmem, dah, dwh, idesc);
+            else mma_f16_s<false>(d_tmem, dah, dwh, idesc);
+        }
+    }
+}
+template <bool SPLIT, int ID, int C, int NCH>
+__device__ __forceinline__ void issue_tiles(SmemTC<SPLIT> &s, uint32_t d_tmem, uint32_t idesc) {
+    if constexpr (C < NCH) {
+        constexpr int stage = ID % W_NSTAGE;
+        mbar_wait(&s.bar_full[stage], (ID / W_NSTAGE) & 1);
+        fence_after_sync();
+        if (elect_one()) issue_tile_mmas<SPLIT, ID, (C > 0)>(s, C, d_tmem, idesc);
+        __syncwarp();
+        issue_tiles<SPLIT, ID + 1, C + 1, NCH>(s, d_tmem, idesc);
+    }
+}
+
+// Warp 0 (all lanes, converged): issue one layer = tiles ID0 .. ID0+NCH-1 against A tiles 0,1,.. (the K16 SH tile for the
+// k16 chunk), then commit to the accumulator barrier.
+template <bool SPLIT, int ID0, int NCH>
+__device__ __forceinline__ void issue_layer(SmemTC<SPLIT> &s, uint32_t d_tmem, uint32_t idesc) {
     fence_after_sync();
-    if (tid == 0)
-        for (int c = 0; c < nchunks; ++c) issue_load<SPLIT>(t, s, st.consumed + c + W_NSTAGE);
-    st.consumed += nchunks;
+    issue_tiles<SPLIT, ID0, 0, NCH>(s, d_tmem, idesc);
+    if (elect_one()) mma_commit(&s.bar_acc);
+    __syncwarp();
+}
+
+// All threads: wait for the accumulator; warp 0 then refills the weight stages the layer has released.
+template <bool SPLIT, int ID0, int NCH>
+__device__ __forceinline__ void wait_acc(const HeadTcArgs &t, SmemTC<SPLIT> &s, uint32_t &acc_uses, int warp) {
+    mbar_wait(&s.bar_acc, acc_uses & 1);
+    acc_uses += 1;
+    fence_after_sync();
+    if (warp == 0) {
+        if (elect_one()) issue_loads<SPLIT, ID0 + W_NSTAGE, NCH>(t, s);
+        __syncwarp();
+    }
 }
 
 // Epilogue of a 128-wide layer: thread (row, half) reads 64 accumulator columns (two passes of 32), applies bias/ReLU and
@@ -154,6 +192,50 @@ __device__ __noinline__ void epilogue_wide(unsigned char *a_hi, unsigned char *a
     }
 }
 
+// fp16-oct fast path: EIGHT consecutive levels of a 3-D grid for one sample -> 16 features (two operand chunks).
+// All eight 32-byte loads (one sm_100 256-bit LDG per oct: half the L1 wavefronts of two 128-bit loads) are issued before
+// the first is consumed, so the thread pays one L2 round trip per table.  Out of line on purpose (I-cache, register budget of the 2-CTA kernel).
+__device__ __noinline__ void lookup8o(const GridMeta &gm, const uint4 *__restrict__ octs, int l0, float u, float v, float w, float (&f)[16]) {
+    float fx[8], fy[8], fz[8];
+    uint4 lo4[8], hi4[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int l = l0 + j;
+        const float s = gm.scale[l];
+        float px = __fadd_rn(__fmul_rn(u, s), gm.align_off), py = __fadd_rn(__fmul_rn(v, s), gm.align_off),
+              pz = __fadd_rn(__fmul_rn(w, s), gm.align_off);
+        const float x0 = floorf(px), y0 = floorf(py), z0 = floorf(pz);
+        px -= x0; py -= y0; pz -= z0;
+        if (gm.interp == 1) {
+            px = px * px * (3.0f - 2.0f * px);
+            py = py * py * (3.0f - 2.0f * py);
+            pz = pz * pz * (3.0f - 2.0f * pz);
+        }
+        fx[j] = px; fy[j] = py; fz[j] = pz;
+        const uint32_t q = grid_mod(gm, l, (uint32_t)x0 + (uint32_t)y0 * gm.mul1[l] + (uint32_t)z0 * gm.mul2[l]);
+        ldg256(octs + 2 * ((size_t)gm.offset[l] + q), lo4[j], hi4[j]);   // the whole 32-byte oct in one request
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t c[8] = {lo4[j].x, lo4[j].y, lo4[j].z, lo4[j].w, hi4[j].x, hi4[j].y, hi4[j].z, hi4[j].w};
+        const float wx[2] = {1.0f - fx[j], fx[j]}, wy[2] = {1.0f - fy[j], fy[j]}, wz[2] = {1.0f - fz[j], fz[j]};
+        float ax = 0.f, ay = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 e = __half22float2(*reinterpret_cast<const __half2 *>(&c[i]));
+            const float wgt = wx[i & 1] * wy[(i >> 1) & 1] * wz[(i >> 2) & 1];
+            ax += wgt * e.x;
+            ay += wgt * e.y;
+        }
+        f[2 * j] = ax;
+        f[2 * j + 1] = ay;
+    }
+    if (u < 0.f || u > 1.f || v < 0.f || v > 1.f || w < 0.f || w > 1.f) {   // outside the grid: zeros (gridencoder.cu:108-118)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = 0.f;
+    }
+}
+
 // Four consecutive levels of a grid -> 8 features (one 16-byte operand chunk).  Out of line on purpose (I-cache).
 __device__ __noinline__ void lookup4(const GridMeta &gm, const float2 *__restrict__ table, const float4 *__restrict__ quads,
                                      const uint4 *__restrict__ octs, int l0, float u, float v, float w, float (&f)[8]) {
@@ -198,11 +280,11 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = s.tmem_base;
-    if (tid == 0)
-        for (uint32_t q = 0; q < W_NSTAGE; ++q) issue_load<SPLIT>(t, s, q);
-    Stream st;
-    st.consumed = 0;
-    st.acc_uses = 0;
+    if (warp == 0) {
+        if (elect_one()) issue_loads<SPLIT, 0, W_NSTAGE>(t, s);
+        __syncwarp();
+    }
+    uint32_t acc_uses = 0;   // completed accumulator hand-offs (uniform across the CTA)
     const uint32_t idesc128 = make_idesc(BF16 ? 1 : 0, 128), idesc144 = make_idesc(BF16 ? 1 : 0, 144);
     const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
 
@@ -236,16 +318,28 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
                 vv = __fdiv_rn(__fadd_rn(s.sy[slot], mc.bound), inv2b);
                 w = __fdiv_rn(__fadd_rn(s.sz[slot], mc.bound), inv2b);
             }
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {   // thread (slot, lg) owns levels lg*8 .. lg*8+7 = operand chunks 2lg, 2lg+1
-                float f[8];
-                if (v) lookup4(a.pos_gm, a.pos_tab, a.pos_quads, a.pos_octs, lg * 8 + c * 4, u, vv, w, f);
+            if (a.pos_octs) {   // thread (slot, lg) owns levels lg*8 .. lg*8+7 = operand chunks 2lg, 2lg+1
+                float f[16];
+                if (v) lookup8o(a.pos_gm, a.pos_octs, lg * 8, u, vv, w, f);
                 else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = 0.f;
+                    for (int i = 0; i < 16; ++i) f[i] = 0.f;
                 }
-                store_chunk<BF16, SPLIT>(s.a_hi[0], s.a_lo[0], sw128_off(slot, 2 * lg + c), f);
-                tmem_st8(tmem + (lane_base << 16) + TMEM_P + (uint32_t)(lg * 16 + c * 8), f);
+                store_chunk<BF16, SPLIT>(s.a_hi[0], s.a_lo[0], sw128_off(slot, 2 * lg), &f[0]);
+                store_chunk<BF16, SPLIT>(s.a_hi[0], s.a_lo[0], sw128_off(slot, 2 * lg + 1), &f[8]);
+                tmem_st16(tmem + (lane_base << 16) + TMEM_P + (uint32_t)(lg * 16), f);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    float f[8];
+                    if (v) lookup4(a.pos_gm, a.pos_tab, a.pos_quads, a.pos_octs, lg * 8 + c * 4, u, vv, w, f);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = 0.f;
+                    }
+                    store_chunk<BF16, SPLIT>(s.a_hi[0], s.a_lo[0], sw128_off(slot, 2 * lg + c), f);
+                    tmem_st8(tmem + (lane_base << 16) + TMEM_P + (uint32_t)(lg * 16 + c * 8), f);
+                }
             }
             // cond values [lg*32, lg*32+32) sit at k = 32 + lg*32 + i: lg 0 -> tile0 chunks 4..7, lg 1 -> tile1 chunks 0..3
             const float4 *cf = reinterpret_cast<const float4 *>(a.cond_feat + (size_t)s.frame[slot] * 64 + lg * 32);
@@ -269,14 +363,14 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
         PH(1)   // position gather + cond + park
 
         // ---- ambient net 96 -> 128 -> 128 -> 3 ----
-        if (tid == 0) issue_layer<SPLIT>(t, s, st, 2, tmem, idesc128);
-        wait_acc<SPLIT>(t, s, st, 2, tid);
+        if (warp == 0) issue_layer<SPLIT, 0, 2>(s, tmem, idesc128);
+        wait_acc<SPLIT, 0, 2>(t, s, acc_uses, warp);
         PH(2)   // MMA issue + wait (ambient L0)
         epilogue_wide<BF16, SPLIT, true, false, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr, nullptr, nullptr);
         fence_async_smem(); fence_before_sync(); __syncthreads();
         PH(3)   // epilogue (ambient L0) + barrier
-        if (tid == 0) issue_layer<SPLIT>(t, s, st, 2, tmem, idesc128);
-        wait_acc<SPLIT>(t, s, st, 2, tid);
+        if (warp == 0) issue_layer<SPLIT, 2, 2>(s, tmem, idesc128);
+        wait_acc<SPLIT, 2, 2>(t, s, acc_uses, warp);
         PH(4)   // MMA (ambient L1)
         // ambient L1 epilogue fused with the 3-wide ambient output layer (fp32 dot products straight from the accumulators)
         epilogue_wide<BF16, SPLIT, true, false, true>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr, s.nw, s.part);
@@ -299,34 +393,49 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
                 vv = __fdiv_rn(__fadd_rn(s.amb[TM + slot], 1.0f), 2.0f);
                 w = __fdiv_rn(__fadd_rn(s.amb[2 * TM + slot], 1.0f), 2.0f);
             }
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                float f[8];
-                tmem_ld8(tmem + (lane_base << 16) + TMEM_P + (uint32_t)(lg * 16 + c * 8), f);
+            {   // parked position features back into tile 0, k[0,32)
+                float p16[16];
+                tmem_ld16(tmem + (lane_base << 16) + TMEM_P + (uint32_t)(lg * 16), p16);
                 wait_ld();
-                store_chunk<BF16, SPLIT>(s.a_hi[0], s.a_lo[0], sw128_off(slot, 2 * lg + c), f);
-                if (v) lookup4(a.amb_gm, a.amb_tab, a.amb_quads, a.amb_octs, lg * 8 + c * 4, u, vv, w, f);
+                store_chunk<BF16, SPLIT>(s.a_hi[0], s.a_lo[0], sw128_off(slot, 2 * lg), &p16[0]);
+                store_chunk<BF16, SPLIT>(s.a_hi[0], s.a_lo[0], sw128_off(slot, 2 * lg + 1), &p16[8]);
+            }
+            if (a.amb_octs) {
+                float f[16];
+                if (v) lookup8o(a.amb_gm, a.amb_octs, lg * 8, u, vv, w, f);
                 else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = 0.f;
+                    for (int i = 0; i < 16; ++i) f[i] = 0.f;
                 }
-                store_chunk<BF16, SPLIT>(s.a_hi[0], s.a_lo[0], sw128_off(slot, 4 + 2 * lg + c), f);
+                store_chunk<BF16, SPLIT>(s.a_hi[0], s.a_lo[0], sw128_off(slot, 4 + 2 * lg), &f[0]);
+                store_chunk<BF16, SPLIT>(s.a_hi[0], s.a_lo[0], sw128_off(slot, 4 + 2 * lg + 1), &f[8]);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    float f[8];
+                    if (v) lookup4(a.amb_gm, a.amb_tab, a.amb_quads, a.amb_octs, lg * 8 + c * 4, u, vv, w, f);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = 0.f;
+                    }
+                    store_chunk<BF16, SPLIT>(s.a_hi[0], s.a_lo[0], sw128_off(slot, 4 + 2 * lg + c), f);
+                }
             }
         }
         fence_async_smem(); fence_before_sync(); __syncthreads();
         PH(7)   // ambient gather + unpark
 
         // ---- sigma net 64 -> 128 -> 128 -> (128 geo + sigma) ----
-        if (tid == 0) issue_layer<SPLIT>(t, s, st, 1, tmem, idesc128);
-        wait_acc<SPLIT>(t, s, st, 1, tid);
+        if (warp == 0) issue_layer<SPLIT, 4, 1>(s, tmem, idesc128);
+        wait_acc<SPLIT, 4, 1>(t, s, acc_uses, warp);
         epilogue_wide<BF16, SPLIT, true, false, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr, nullptr, nullptr);
         fence_async_smem(); fence_before_sync(); __syncthreads();
-        if (tid == 0) issue_layer<SPLIT>(t, s, st, 2, tmem, idesc128);
-        wait_acc<SPLIT>(t, s, st, 2, tid);
+        if (warp == 0) issue_layer<SPLIT, 5, 2>(s, tmem, idesc128);
+        wait_acc<SPLIT, 5, 2>(t, s, acc_uses, warp);
         epilogue_wide<BF16, SPLIT, true, false, false>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, nullptr, nullptr, nullptr);
         fence_async_smem(); fence_before_sync(); __syncthreads();
-        if (tid == 0) issue_layer<SPLIT>(t, s, st, 2, tmem, idesc144);
-        wait_acc<SPLIT>(t, s, st, 2, tid);
+        if (warp == 0) issue_layer<SPLIT, 7, 2>(s, tmem, idesc144);
+        wait_acc<SPLIT, 7, 2>(t, s, acc_uses, warp);
         if (tid < TM) {   // column 128 = sigma logit (weight row 0 was packed last); sigma = density_scale * exp(h)
             float o[16];
             tmem_ld16(tmem + (lane_base << 16) + 128u, o);
@@ -347,8 +456,8 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
 
         PH(8)   // sigma net: 3 MMA layers + 3 epilogues
         // ---- color net (128 geo + 16 SH [+ folded individual code]) -> 128 -> 3 ----
-        if (tid == 0) issue_layer<SPLIT>(t, s, st, 3, tmem, idesc128);
-        wait_acc<SPLIT>(t, s, st, 3, tid);
+        if (warp == 0) issue_layer<SPLIT, 9, 3>(s, tmem, idesc128);
+        wait_acc<SPLIT, 9, 3>(t, s, acc_uses, warp);
         // color L0 epilogue fused with the 3-wide rgb output layer
         epilogue_wide<BF16, SPLIT, true, true, true>(&s.a_hi[0][0], &s.a_lo[0][0], tmem, tid, s.bias, s.nw + 3 * 128, s.part);
         fence_before_sync();
@@ -370,10 +479,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
     }
 
     // drain the prefetched weight tiles, then release TMEM
-    for (uint32_t q = 0; q < W_NSTAGE; ++q) {
-        const uint32_t seq = st.consumed + q;
-        mbar_wait(&s.bar_full[seq % W_NSTAGE], (seq / W_NSTAGE) & 1);
-    }
+    for (uint32_t q = 0; q < W_NSTAGE; ++q) mbar_wait(&s.bar_full[q], 0);   // tiles 0..2 of a batch that never comes
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
@@ -386,6 +492,7 @@ size_t head_tc_smem_bytes(bool split) { return (split ? sizeof(SmemTC<true>) : s
 cudaError_t launch_head_tc(const HeadArgs &a, const HeadTcArgs &t, int precision, int total_hint, cudaStream_t st) {
     const bool split = precision == BF16_X3;
     int blocks = sm_count() * (split ? 1 : 2);   // single-pass kernels: two resident CTAs per SM
+    if (getenv("GFPP_ONE_CTA")) blocks = sm_count();   // diagnostics: phase timings without the co-resident CTA
     if (total_hint >= 0) {
         const int need = (total_hint + TM - 1) / TM;
         if (need < blocks) blocks = need > 0 ? need : 1;

@@ -126,6 +126,24 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, accumulate flag known at compile time (no predicate set-up on the issue path)
+template <bool ACC>
+__device__ __forceinline__ void mma_f16_s(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    if (ACC)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc)
+                     : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                     "l"(a_desc), "l"(b_desc), "r"(idesc)
+                     : "memory");
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(unsigned long long *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

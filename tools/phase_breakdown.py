@@ -3,6 +3,7 @@ import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__
 from genefaceplusplus_b200 import _capi, scene as scn
 from genefaceplusplus_b200.renderer import RADNeRFTorso
 prec = sys.argv[1] if len(sys.argv)>1 else 'fp16'
+if '--one-cta' in sys.argv: os.environ['GFPP_ONE_CTA'] = '1'   # phase timings without the co-resident CTA
 sc = scn.Scene(H=512,W=512,T=20,torso=True,density_scale=8.0)
 m = RADNeRFTorso(sc.hparams); m.load_state_dict(sc.state); m.density_scale=8.0; m.mlp_precision=prec; m=m.cuda().eval()
 poses = torch.stack([sc.pose(t) for t in range(20)])
