@@ -185,7 +185,7 @@ WorkLayout work_layout(uint32_t F, uint32_t N, uint32_t max_steps) {
     W.wsum = take(FN * 4);
     W.depth = take(FN * 4);
     W.survivors = take(FN * 4);
-    W.hits = take(FN * 8);
+    W.hits = take(FN * 64);   // HitRecord (head_common.cuh)
     W.zero_begin = o;
     W.hist = take((size_t)F * (max_steps + 2) * 4);
     W.counters = take(16 * 4);
@@ -580,7 +580,7 @@ int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfp
     a.survivors = (int *)(ws + W.survivors);
     int *counters = (int *)(ws + W.counters);
     a.n_survivors = counters + 2;
-    a.hits = (int2 *)(ws + W.hits);
+    a.hits = (uint4 *)(ws + W.hits);
     a.n_hits = counters + 3;
     a.B_total = (int *)(ws + W.B_total);
     a.valid_samples = (int *)(ws + W.valid);

@@ -323,6 +323,13 @@ __device__ __forceinline__ void ldg256(const uint4 *p, uint4 &lo, uint4 &hi) {
     lo.x = (uint32_t)a; lo.y = (uint32_t)(a >> 32); lo.z = (uint32_t)b; lo.w = (uint32_t)(b >> 32);
     hi.x = (uint32_t)c2; hi.y = (uint32_t)(c2 >> 32); hi.z = (uint32_t)d; hi.w = (uint32_t)(d >> 32);
 }
+// same, streaming past L1 (no line allocated): the fp16 oct gathers of the 2-CTA kernel, which leaves L1 only ~28 KB
+__device__ __forceinline__ void ldg256_na(const uint4 *p, uint4 &lo, uint4 &hi) {
+    unsigned long long a, b, c2, d;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c2), "=l"(d) : "l"(p));
+    lo.x = (uint32_t)a; lo.y = (uint32_t)(a >> 32); lo.z = (uint32_t)b; lo.w = (uint32_t)(b >> 32);
+    hi.x = (uint32_t)c2; hi.y = (uint32_t)(c2 >> 32); hi.z = (uint32_t)d; hi.w = (uint32_t)(d >> 32);
+}
 __device__ __forceinline__ float2 grid_lookup3q(const GridMeta &gm, const float4 *__restrict__ quads, int l, float u, float v, float w) {
     if (u < 0.f || u > 1.f || v < 0.f || v > 1.f || w < 0.f || w > 1.f) return make_float2(0.f, 0.f);
     const float s = gm.scale[l];

@@ -28,6 +28,17 @@ struct Slot {
     bool active;
 };
 
+// What k_ray_setup leaves for the persistent kernel: a ray that reaches a first sample, ready to run.  One 64-byte record =
+// two 256-bit loads on adoption instead of hit-id -> pose -> get_rays/near_far/box arithmetic between two CTA barriers.
+struct alignas(32) HitRecord {
+    int gid;
+    float t, px, py, pz, dt;      // first sample (t already advanced past it)
+    float near, far, far_m;
+    float ox, oy, oz, dx, dy, dz;
+    int pad;
+};
+static_assert(sizeof(HitRecord) == 64, "HitRecord is four 16-byte words");
+
 __device__ __forceinline__ void load_ray(const HeadArgs &a, int frame, int ray, RayGeom &g) {
     if (a.rays_o) {
         const size_t o = ((size_t)frame * a.n_rays + ray) * 3;
@@ -128,21 +139,29 @@ __device__ __forceinline__ int refill_and_publish(const HeadArgs &a, SmemT &s, S
                 const int w = atomicAdd(&s.next, 1);
                 if (w >= s.end) break;
                 int gid;
-                float t_pre = 0.f;
-                if (a.pass == 2) gid = a.survivors[w];
-                else { const int2 hv = a.hits[w]; gid = hv.x; t_pre = __int_as_float(hv.y); }
-                sl.gid = gid;
-                sl.frame = gid / a.n_rays;
-                const int ray = gid - sl.frame * a.n_rays;
-                load_ray(a, sl.frame, ray, sl.g);
-                near_far(sl.g, a.aabb, a.min_near, sl.near, sl.far);
+                HitRecord hr;
+                if (a.pass == 2) {
+                    gid = a.survivors[w];
+                    sl.gid = gid;
+                    sl.frame = gid / a.n_rays;
+                    load_ray(a, sl.frame, gid - sl.frame * a.n_rays, sl.g);
+                    near_far(sl.g, a.aabb, a.min_near, sl.near, sl.far);
+                } else {
+                    uint4 *q = reinterpret_cast<uint4 *>(&hr);
+                    ldg256(a.hits + 4 * (size_t)w, q[0], q[1]);
+                    ldg256(a.hits + 4 * (size_t)w + 2, q[2], q[3]);
+                    gid = hr.gid;
+                    sl.gid = gid;
+                    sl.frame = gid / a.n_rays;
+                }
                 bool live;
                 if (a.pass == 1) {
-                    // k_ray_setup already marched this ray to its first sample: adopt it in O(1)
+                    // k_ray_setup already set this ray up and marched it to its first sample: adopt the record
+                    ray_geom_init(sl.g, hr.ox, hr.oy, hr.oz, hr.dx, hr.dy, hr.dz);
+                    sl.near = hr.near; sl.far = hr.far; sl.far_m = hr.far_m;
+                    sl.t = hr.t; sl.px = hr.px; sl.py = hr.py; sl.pz = hr.pz; sl.dt = hr.dt;
                     sl.ws = 0.f; sl.depth = 0.f; sl.r = sl.gch = sl.b = 0.f;
                     sl.nsamp = 0; sl.cap = a.max_steps;
-                    (void)may_hit_occupied(have_box, occ_lo, occ_hi, sl.g, sl.near, sl.far, sl.far_m);
-                    sample_at(mc, sl.g, t_pre, sl.t, sl.px, sl.py, sl.pz, sl.dt);
                     live = true;
                 } else {
                     const size_t g = (size_t)gid;

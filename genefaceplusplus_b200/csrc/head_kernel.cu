@@ -400,7 +400,15 @@ __global__ void __launch_bounds__(256) k_ray_setup(const __grid_constant__ HeadA
             int base = 0;
             if (grp.thread_rank() == 0) base = atomicAdd(a.n_hits, (int)grp.size());
             base = grp.shfl(base, 0);
-            a.hits[base + grp.thread_rank()] = make_int2(gid, __float_as_int(sl.t));
+            HitRecord hr;
+            hr.gid = gid; hr.pad = 0;
+            sample_at(mc, sl.g, sl.t, hr.t, hr.px, hr.py, hr.pz, hr.dt);
+            hr.near = sl.near; hr.far = sl.far; hr.far_m = sl.far_m;
+            hr.ox = sl.g.ox; hr.oy = sl.g.oy; hr.oz = sl.g.oz; hr.dx = sl.g.dx; hr.dy = sl.g.dy; hr.dz = sl.g.dz;
+            uint4 *dst = a.hits + 4 * (size_t)(base + grp.thread_rank());
+            const uint4 *src = reinterpret_cast<const uint4 *>(&hr);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = src[i];
         } else {
             sl.ws = 0.f; sl.depth = 0.f; sl.r = sl.gch = sl.b = 0.f;
             finalize_ray(a, sl, true);

@@ -41,7 +41,7 @@ struct HeadArgs {
     float *depth;                   // [F,N]
     float *rays_t;                  // [F,N] resume point of rays that outlive max_steps
     int *hist;                      // [F, max_steps+2] death-index histogram
-    int2 *hits;                     // [F*N] (ray id, bits of t_pre): rays that reach a first sample, from k_ray_setup
+    uint4 *hits;                    // [F*N][4] 64-byte records of the rays that reach a first sample, from k_ray_setup (HitRecord)
     int *n_hits;                    // [1]
     int *survivors;                 // [F*N] global ray ids still alive after max_steps samples
     int *n_survivors;               // [1]
