@@ -129,7 +129,7 @@ static_assert(sizeof(ModelHost) <= sizeof(gfpp_model), "gfpp_model opaque storag
 constexpr uint32_t kMagic = 0x67667070u;  // "gfpp"
 
 struct PackedLayout {
-    size_t wide, narrow, wd0, wd1, wd2, wc0, wc1, wc2, occ, coarse, tc_hi, tc_lo, tcn_hi, tcn_lo, pos_quads, amb_quads, total;
+    size_t wide, narrow, wd0, wd1, wd2, wc0, wc1, wc2, occ, coarse, tc_hi, tc_lo, pos_quads, amb_quads, total;
 };
 
 // tensor-core weight stream: kHeadTcChunks (head_kernel.cuh)
@@ -162,8 +162,6 @@ PackedLayout packed_layout(uint32_t cascade = 8, uint32_t grid_size = 128, size_
     for (int c = 0; c < HEAD_TC_NCHUNK; ++c) tcb += (size_t)tc_chunk_bytes(c);
     L.tc_hi = take(tcb / 4);
     L.tc_lo = take(tcb / 4);
-    L.tcn_hi = take(4 * 2048 / 4);
-    L.tcn_lo = take(4 * 2048 / 4);
     L.pos_quads = take(pos_entries * 8);   // 32 bytes per entry
     L.amb_quads = take(amb_entries * 8);
     L.total = o;
@@ -449,17 +447,12 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
         const int bf16 = d->mlp_precision != 1;
         const bool split = d->mlp_precision == 2;
         unsigned char *thi = (unsigned char *)(base + L.tc_hi), *tlo = (unsigned char *)(base + L.tc_lo);
-        unsigned char *nhi = (unsigned char *)(base + L.tcn_hi), *nlo = (unsigned char *)(base + L.tcn_lo);
         CKN(cudaMemsetAsync(base + L.tc_hi, 0, L.pos_quads - L.tc_hi, st));
         const float *lw[6] = {d->ambient_w[0], d->ambient_w[1], d->sigma_w[0], d->sigma_w[1], d->sigma_w[2], d->color_w[0]};
         const int lld[6] = {96, 128, 64, 128, 128, col0_in};
         int boff = 0;
         for (int c = 0; c < HEAD_TC_NCHUNK; ++c) {
             const TcChunk &k = kTc[c];
-            m.tc.chunk_off[c] = boff;
-            m.tc.chunk_bytes[c] = tc_chunk_bytes(c);
-            m.tc.chunk_ksteps[c] = k.k16 ? 1 : k.kc / 16;
-            m.tc.chunk_k16[c] = k.k16;
             if (k.layer == 4) {  // sigma L2: geo rows (W rows 1..128) first, the sigma row (W row 0) as row 128
                 CK(launch_pack_tc_tile(lw[4], 128, 1, k.col0, 128, k.kc, 0, 0, bf16, thi + boff, split ? tlo + boff : nullptr, st));
                 CK(launch_pack_tc_tile(lw[4], 128, 0, k.col0, 1, k.kc, 128, 0, bf16, thi + boff, split ? tlo + boff : nullptr, st));
@@ -468,11 +461,7 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
             }
             boff += tc_chunk_bytes(c);
         }
-        for (int kt = 0; kt < 2; ++kt) {
-            CK(launch_pack_tc_tile(d->ambient_w[2], 128, 0, kt * 64, amb_dim, 64, 0, 0, bf16, nhi + kt * 2048, split ? nlo + kt * 2048 : nullptr, st));
-            CK(launch_pack_tc_tile(d->color_w[1], 128, 0, kt * 64, 3, 64, 0, 0, bf16, nhi + (2 + kt) * 2048, split ? nlo + (2 + kt) * 2048 : nullptr, st));
-        }
-        m.tc.w_hi = thi; m.tc.w_lo = tlo; m.tc.narrow_hi = nhi; m.tc.narrow_lo = nlo;
+        m.tc.w_hi = thi; m.tc.w_lo = tlo;
     }
 
     // fp16 mode: fp16 "octs" (one 32-byte sector per sample-level; tables rounded to fp16 like the reference under

@@ -374,36 +374,7 @@ __device__ __forceinline__ float2 grid_lookup3q(const GridMeta &gm, const float4
 //   O[i] = { T[i], T[i+1], T[i+m1], T[i+m1+1], T[i+m2], T[i+m2+1], T[i+m2+m1], T[i+m2+m1+1] }   (indices mod the level size)
 // Table values are rounded to fp16 -- exactly what the reference does under autocast (gridencoder/grid.py:43-44: the
 // embeddings are cast to half) -- and interpolated in fp32.  Used together with fp16 MMA operands, never in the
-// fp32 / bf16x3 modes.
-__device__ __forceinline__ float2 grid_lookup3o(const GridMeta &gm, const uint4 *__restrict__ octs, int l, float u, float v, float w) {
-    if (u < 0.f || u > 1.f || v < 0.f || v > 1.f || w < 0.f || w > 1.f) return make_float2(0.f, 0.f);
-    const float s = gm.scale[l];
-    float px = __fadd_rn(__fmul_rn(u, s), gm.align_off), py = __fadd_rn(__fmul_rn(v, s), gm.align_off),
-          pz = __fadd_rn(__fmul_rn(w, s), gm.align_off);
-    const float fx0 = floorf(px), fy0 = floorf(py), fz0 = floorf(pz);
-    const uint32_t gx = (uint32_t)fx0, gy = (uint32_t)fy0, gz = (uint32_t)fz0;
-    px -= fx0; py -= fy0; pz -= fz0;
-    if (gm.interp == 1) {
-        px = px * px * (3.0f - 2.0f * px);
-        py = py * py * (3.0f - 2.0f * py);
-        pz = pz * pz * (3.0f - 2.0f * pz);
-    }
-    const uint32_t q = grid_mod(gm, l, gx + gy * gm.mul1[l] + gz * gm.mul2[l]);
-    uint4 lo4, hi4;
-    ldg256(octs + 2 * ((size_t)gm.offset[l] + q), lo4, hi4);
-    const uint32_t c[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-    const float wx[2] = {1.0f - px, px}, wy[2] = {1.0f - py, py}, wz[2] = {1.0f - pz, pz};
-    float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float2 e = __half22float2(*reinterpret_cast<const __half2 *>(&c[i]));
-        const float wgt = wx[i & 1] * wy[(i >> 1) & 1] * wz[(i >> 2) & 1];
-        acc.x += wgt * e.x;
-        acc.y += wgt * e.y;
-    }
-    return acc;
-}
-
+// fp32 / bf16x3 modes.  Reader: lookup8o (head_tc_kernel.cu); writer: k_pack_octs (ops_kernels.cu).
 __device__ __forceinline__ float2 grid_lookup2(const GridMeta &gm, const float2 *__restrict__ table, int l, float u,
                                                float v) {
     if (u < 0.f || u > 1.f || v < 0.f || v > 1.f) return make_float2(0.f, 0.f);

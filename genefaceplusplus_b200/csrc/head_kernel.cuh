@@ -70,12 +70,7 @@ constexpr int head_tc_chunk_bytes(int c) { return kHeadTcChunks[c].rows * (kHead
 constexpr int head_tc_chunk_off(int c) { return c == 0 ? 0 : head_tc_chunk_off(c - 1) + head_tc_chunk_bytes(c - 1); }
 constexpr int head_tc_chunk_ksteps(int c) { return kHeadTcChunks[c].k16 ? 1 : kHeadTcChunks[c].kc / 16; }
 struct HeadTcArgs {
-    const unsigned char *w_hi, *w_lo;       // streamed tiles, hi and lo images with identical layout
-    int chunk_off[HEAD_TC_NCHUNK];          // byte offset of each tile
-    int chunk_bytes[HEAD_TC_NCHUNK];        // rows * 128 (SW128 tile) or rows * 32 (K16 tile)
-    int chunk_ksteps[HEAD_TC_NCHUNK];       // MMA k-steps (16 elements each) the tile holds
-    int chunk_k16[HEAD_TC_NCHUNK];          // 1: K16 (no-swizzle) tile paired with the SH operand tile
-    const unsigned char *narrow_hi, *narrow_lo;  // 4 x [16 x 64] SW128 tiles: ambient-out k-tiles 0,1, color-out k-tiles 0,1
+    const unsigned char *w_hi, *w_lo;       // the 12 streamed tiles back to back (head_tc_chunk_off), hi and lo images with identical layout
 };
 cudaError_t launch_head_tc(const HeadArgs &a, const HeadTcArgs &t, int precision, int total_hint, cudaStream_t st);
 size_t head_tc_smem_bytes(bool split);

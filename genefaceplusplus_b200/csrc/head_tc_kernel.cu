@@ -251,13 +251,13 @@ __device__ __forceinline__ void stage_level_meta(const GridMeta &gm, uint4 *lvl,
     }
 }
 
-// Four consecutive levels of a grid -> 8 features (one 16-byte operand chunk).  Out of line on purpose (I-cache).
-__device__ __noinline__ void lookup4(const GridMeta &gm, const float2 *__restrict__ table, const float4 *__restrict__ quads,
-                                     const uint4 *__restrict__ octs, int l0, float u, float v, float w, float (&f)[8]) {
+// Four consecutive levels of a grid -> 8 features (one 16-byte operand chunk): the fp32 quad layout (bf16x3 / bf16 modes) or
+// the reference layout.  Out of line on purpose (I-cache).
+__device__ __noinline__ void lookup4(const GridMeta &gm, const float2 *__restrict__ table, const float4 *__restrict__ quads, int l0,
+                                     float u, float v, float w, float (&f)[8]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float2 g2 = (gm.dim == 3) ? (octs ? grid_lookup3o(gm, octs, l0 + j, u, v, w)
-                                                : (quads ? grid_lookup3q(gm, quads, l0 + j, u, v, w) : grid_lookup3(gm, table, l0 + j, u, v, w)))
+        const float2 g2 = (gm.dim == 3) ? (quads ? grid_lookup3q(gm, quads, l0 + j, u, v, w) : grid_lookup3(gm, table, l0 + j, u, v, w))
                                         : grid_lookup2(gm, table, l0 + j, u, v);
         f[2 * j] = g2.x;
         f[2 * j + 1] = g2.y;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
     extern __shared__ __align__(1024) unsigned char smem_raw_[];
     unsigned char *smem_raw = smem_raw_ + ((1024u - (smem_u32(smem_raw_) & 1023u)) & 1023u);
     SmemTC<SPLIT> &s = *reinterpret_cast<SmemTC<SPLIT> *>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
 
     // ---- one-time setup ----
     MarchConst mc = a.mc;
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
                     float f[8];
-                    if (v) lookup4(a.pos_gm, a.pos_tab, a.pos_quads, a.pos_octs, lg * 8 + c * 4, u, vv, w, f);
+                    if (v) lookup4(a.pos_gm, a.pos_tab, a.pos_quads, lg * 8 + c * 4, u, vv, w, f);
                     else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) f[i] = 0.f;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
                     float f[8];
-                    if (v) lookup4(a.amb_gm, a.amb_tab, a.amb_quads, a.amb_octs, lg * 8 + c * 4, u, vv, w, f);
+                    if (v) lookup4(a.amb_gm, a.amb_tab, a.amb_quads, lg * 8 + c * 4, u, vv, w, f);
                     else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) f[i] = 0.f;

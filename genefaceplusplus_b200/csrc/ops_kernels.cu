@@ -198,7 +198,7 @@ __global__ void k_pack_quads(GridMeta gm, const float2 *__restrict__ table, floa
     }
 }
 
-// ---- fp16 oct layout of a tiled 3-D grid (common.cuh: grid_lookup3o) ----
+// ---- fp16 oct layout of a tiled 3-D grid (common.cuh; read by lookup8o in head_tc_kernel.cu) ----
 __global__ void k_pack_octs(GridMeta gm, const float2 *__restrict__ table, uint4 *__restrict__ octs, uint32_t total) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int l = 0;
