@@ -101,6 +101,7 @@ class _AudioAttNet(nn.Module):
 # ------------------------------------------------------------------------------------------------ head model
 class RADNeRF(nn.Module):
     has_torso = False
+    forwards_eye_area = True   # renderer.py:308 passes eye_area_percent on; radnerf_torso.py:86-106 lets it fall into **kwargs
 
     def __init__(self, hparams):
         super().__init__()
@@ -135,14 +136,19 @@ class RADNeRF(nn.Module):
             self.cond_in_dim = {"lm68": 68 * 3, "lm131": 131 * 3, "lm468": 468 * 3}[hp.get("nerf_keypoint_mode", "lm68")]
         else:
             raise NotImplementedError()
-        if hp.get("add_eye_blink_cond", False):
-            raise NotImplementedError("add_eye_blink_cond belongs to the SR configs (SURVEY.md 8(f) rank 2)")
         self.cond_out_dim = hp["cond_out_dim"] // 2 * 2
         self.cond_win_size = hp["cond_win_size"]
         self.smo_win_size = hp["smo_win_size"]
         if self.cond_win_size != 1:
             raise NotImplementedError("cond_win_size != 1 (audio-window conditioning) is not on the May path")
         self.cond_prenet = _AudioNet(self.cond_in_dim, self.cond_out_dim)
+        # eye-blink conditioning of the SR-era configs (radnerf.py:40-47): same parameter names
+        self.add_eye_blink_cond = bool(hp.get("add_eye_blink_cond", False))
+        if self.add_eye_blink_cond:
+            self.eye_blink_dim = int(hp["eye_blink_dim"])
+            self.blink_embedding = nn.Embedding(1, self.cond_out_dim // 2)
+            self.blink_encoder = nn.Sequential(nn.Linear(self.cond_out_dim // 2, self.cond_out_dim // 2),
+                                               nn.Linear(self.cond_out_dim // 2, self.eye_blink_dim))
         self.with_att = hp["with_att"]
         if self.with_att:
             self.cond_att_net = _AudioAttNet(self.cond_out_dim, self.smo_win_size)
@@ -186,13 +192,30 @@ class RADNeRF(nn.Module):
         # fp32 end to end: no autocast, no TF32 convolutions (the 1e-3 parity bar is against the fp32 oracle)
         with torch.autocast("cuda", enabled=False):
             feat = self.cond_prenet(cond.float())
+            if self.add_eye_blink_cond:
+                feat = self._add_blink(feat, eye_area_percent, 1)
             if self.with_att:
                 feat = self.cond_att_net(feat)
         return feat
 
-    def cal_cond_feat_clip(self, cond_seq):
+    def _add_blink(self, feat, eye_area_percent, n_frames):
+        """radnerf.py:97-103: blink_encoder(blink_embedding[0] * eye_area_percent) is added to the first eye_blink_dim
+        channels of EVERY row of the frame's window (zero-padded rows included); None means 0 %.  feat: [n_frames * S, C]
+        (S window rows per frame, frame-major) or [S, C] for one frame; eye_area_percent: scalar / [n_frames]."""
+        E = self.eye_blink_dim
+        if eye_area_percent is None:
+            pct = torch.zeros(n_frames, 1, device=feat.device, dtype=feat.dtype)
+        else:
+            pct = torch.as_tensor(eye_area_percent, device=feat.device, dtype=feat.dtype).reshape(n_frames, 1)
+        blink = self.blink_encoder(self.blink_embedding.weight[0].reshape(1, -1) * pct)        # [n_frames, E]
+        rows = feat.shape[0] // n_frames
+        out = feat.clone()
+        out[:, :E] = feat[:, :E] + blink.repeat_interleave(rows, dim=0)
+        return out
+
+    def cal_cond_feat_clip(self, cond_seq, eye_area_percent=None):
         """All frames at once: cond_seq [T,1,C] -> [T,64]; windows as get_audio_features(att_mode=2)
-        (modules/radnerfs/utils.py:86-102: centred, zero-padded)."""
+        (modules/radnerfs/utils.py:86-102: centred, zero-padded).  eye_area_percent: [T] (add_eye_blink_cond models)."""
         with torch.autocast("cuda", enabled=False):
             T = cond_seq.shape[0]
             S = self.smo_win_size
@@ -203,7 +226,10 @@ class RADNeRF(nn.Module):
             xp = torch.cat([pad, x, padr], 0)
             idx = torch.arange(T, device=x.device).unsqueeze(1) + torch.arange(S, device=x.device).unsqueeze(0)
             wins = xp[idx]                                                  # [T,S,C]
-            feat = self.cond_prenet(wins.reshape(T * S, 1, -1)).view(T, S, -1)
+            feat = self.cond_prenet(wins.reshape(T * S, 1, -1))
+            if self.add_eye_blink_cond:
+                feat = self._add_blink(feat, eye_area_percent, T)
+            feat = feat.view(T, S, -1)
             # the reference zero-pads the *window*, and the prenet maps a zero row to f(0) != 0: same here
             if self.with_att:
                 feat = self.cond_att_net.forward_batched(feat)
@@ -368,7 +394,8 @@ class RADNeRF(nn.Module):
         prefix = rays_o.shape[:-1]
         if rays_o.numel() // 3 != int(np.prod(prefix)) or (len(prefix) > 1 and prefix[0] != 1):
             raise ValueError("render() assumes B == 1 (renderer.py:287)")
-        cond_feat = self.cal_cond_feat(cond.to(self.density_bitfield.device), eye_area_percent=eye_area_percent)
+        cond_feat = self.cal_cond_feat(cond.to(self.density_bitfield.device),
+                                       eye_area_percent=eye_area_percent if self.forwards_eye_area else None)
         res = self.render_frames(cond_feat.reshape(1, -1), rays_o=rays_o.reshape(1, -1, 3), rays_d=rays_d.reshape(1, -1, 3),
                                  pose6=poses if self.has_torso else None, bg_coords=bg_coords if self.has_torso else None,
                                  bg_color=bg_color, dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh)
@@ -387,16 +414,17 @@ class RADNeRF(nn.Module):
     # ------------------------------------------------------------------ clip API
     @torch.no_grad()
     def render_clip(self, poses_c2w, intrinsics, H, W, cond_seq=None, cond_feat=None, bg_color=None, bg_coords=None, pose6=None,
-                    dt_gamma=None, max_steps=None, T_thresh=1e-2, frames_per_call=64, out=None, want_stats=False):
-        """Render a clip: poses_c2w [T,4,4], cond_seq [T,1,C] (or precomputed cond_feat [T,64]).
-        Returns rgb [T,H*W,3] on the model's device (fp32, clamped to [0,1])."""
+                    dt_gamma=None, max_steps=None, T_thresh=1e-2, frames_per_call=64, out=None, want_stats=False,
+                    eye_area_percent=None):
+        """Render a clip: poses_c2w [T,4,4], cond_seq [T,1,C] (or precomputed cond_feat [T,64]); eye_area_percent [T] for
+        add_eye_blink_cond models.  Returns rgb [T,H*W,3] on the model's device (fp32, clamped to [0,1])."""
         dev = self.density_bitfield.device
         T = poses_c2w.shape[0]
         hp = self.hparams
         dt_gamma = hp["dt_gamma"] if dt_gamma is None else dt_gamma
         max_steps = hp["max_steps"] if max_steps is None else max_steps
         if cond_feat is None:
-            cond_feat = self.cal_cond_feat_clip(cond_seq.to(dev))
+            cond_feat = self.cal_cond_feat_clip(cond_seq.to(dev), eye_area_percent=eye_area_percent if self.forwards_eye_area else None)
         poses_c2w = poses_c2w.to(dev, torch.float32)
         if self.has_torso and pose6 is None:
             from .scene import convert_poses
@@ -421,6 +449,7 @@ class RADNeRF(nn.Module):
 # ------------------------------------------------------------------------------------------------ torso model
 class RADNeRFTorso(RADNeRF):
     has_torso = True
+    forwards_eye_area = False
 
     def __init__(self, hparams):
         super().__init__(hparams)

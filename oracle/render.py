@@ -61,7 +61,7 @@ class OracleModel:
         self.interp_id = {"linear": 0, "smoothstep": 1}[self.hp["grid_interpolation_type"]]
 
     # ---- conditioning (radnerf.py:88-106; cond_encoder.py:98-180) ----
-    def cal_cond_feat(self, cond):
+    def cal_cond_feat(self, cond, eye_area_percent=None):
         st = self.st
         x = cond.float().permute(0, 2, 1)  # [b, c, t=1]
         for i in (0, 2, 4, 6):
@@ -70,6 +70,14 @@ class OracleModel:
         x = x.squeeze(-1)
         x = F.leaky_relu(F.linear(x, st["cond_prenet.encoder_fc1.0.weight"], st["cond_prenet.encoder_fc1.0.bias"]), 0.02)
         x = F.linear(x, st["cond_prenet.encoder_fc1.2.weight"], st["cond_prenet.encoder_fc1.2.bias"])  # [b, 64]
+        if self.hp.get("add_eye_blink_cond", False):   # radnerf.py:97-103
+            E = self.hp["eye_blink_dim"]
+            pct = torch.zeros(1, 1) if eye_area_percent is None else torch.as_tensor(eye_area_percent, dtype=torch.float32).reshape(1, 1)
+            b = st["blink_embedding.weight"][0].reshape(1, -1) * pct
+            b = F.linear(b, st["blink_encoder.0.weight"], st["blink_encoder.0.bias"])
+            b = F.linear(b, st["blink_encoder.1.weight"], st["blink_encoder.1.bias"])
+            x = x.clone()
+            x[..., :E] = x[..., :E] + b.expand(x[..., :E].shape)
         if not self.hp["with_att"]:
             return x
         seq = x.shape[0]

@@ -65,6 +65,7 @@ def test_unsupported_configs_raise_like_the_reference_would():
         RADNeRF(may_hparams(hidden_dim_sigma=64))
     with pytest.raises(NotImplementedError):
         RADNeRFTorso(may_hparams(torso_head_aware=True))
+    RADNeRF(may_hparams(add_eye_blink_cond=True, eye_blink_dim=2))   # supported since the blink branch was added
 
 
 def test_cond_feat_clip_equals_per_frame(oracle_ops):
@@ -79,6 +80,41 @@ def test_cond_feat_clip_equals_per_frame(oracle_ops):
         ref = orc.cal_cond_feat(scn.cond_window(sc.cond, t))
         assert (feat[t] - ref).abs().max().item() < 1e-5, t
         assert (m.cal_cond_feat(scn.cond_window(sc.cond, t)) - ref).abs().max().item() < 1e-5
+
+
+def test_eye_blink_cond_matches_the_reference_golden():
+    """add_eye_blink_cond (radnerf.py:40-47, 97-103): the golden vectors are the REFERENCE's own
+    cal_cond_feat outputs (oracle/make_blink_golden.py).  Replayed per frame, batched over the clip, and through the oracle."""
+    import os
+    from oracle.render import OracleModel
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cond_blink.npz"))
+    hp = may_hparams(add_eye_blink_cond=True, eye_blink_dim=2)
+    m = RADNeRF(hp).eval()
+    sub = {k[len("state/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}
+    assert {"blink_embedding.weight", "blink_encoder.0.weight", "blink_encoder.0.bias", "blink_encoder.1.weight",
+            "blink_encoder.1.bias"} <= set(sub) and set(sub) <= set(m.state_dict())       # same parameter names as the reference
+    missing, unexpected = m.load_state_dict(sub, strict=False)
+    assert not unexpected
+    cond_seq, eye = torch.from_numpy(g["cond_seq"]), torch.from_numpy(g["eye"])
+    T = eye.shape[0]
+    with torch.no_grad():
+        clip = m.cal_cond_feat_clip(cond_seq[:T] if cond_seq.shape[0] == T else cond_seq, eye_area_percent=eye)
+        clip0 = m.cal_cond_feat_clip(cond_seq)
+    orc = OracleModel(sub, hp)
+    worst = 0.0
+    for t in range(T):
+        win = torch.from_numpy(g[f"f{t}_cond_win"])
+        ref_eye, ref_no = torch.from_numpy(g[f"f{t}_with_eye"]), torch.from_numpy(g[f"f{t}_no_eye"])
+        with torch.no_grad():
+            got = m.cal_cond_feat(win, eye_area_percent=eye[t].reshape(1, 1))
+            got0 = m.cal_cond_feat(win)
+        for a, b in ((got, ref_eye), (got0, ref_no), (clip[t], ref_eye), (clip0[t], ref_no),
+                     (orc.cal_cond_feat(win, eye_area_percent=eye[t]), ref_eye), (orc.cal_cond_feat(win), ref_no)):
+            worst = max(worst, (a - b).abs().max().item())
+        assert (ref_eye - ref_no).abs().max().item() > 1e-3 or eye[t] == 0      # the branch is live in the golden data
+    assert worst < 2e-6, worst
+    # the non-SR torso class never forwards eye_area_percent (radnerf_torso.py:86-106); the head class does (renderer.py:308)
+    assert RADNeRF.forwards_eye_area and not RADNeRFTorso.forwards_eye_area
 
 
 def test_round_schedule_lemma(oracle_ops):
