@@ -14,7 +14,8 @@ import torch
 
 from genefaceplusplus_b200 import scene as scn
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+# render fixtures only (cond_blink.npz holds conditioning vectors: tests/test_host_logic.py)
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith("cond_"))
 
 
 def _meta(z):
