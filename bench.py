@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--density-scale", type=float, default=8.0)
     ap.add_argument("--head-only", action="store_true")
     ap.add_argument("--frames-per-call", type=int, default=50)
-    ap.add_argument("--cpu-frames", type=int, default=1, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the bounded CPU-baseline sample (~3.5 s each on the box)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default=os.environ.get("GFPP_BENCH_PRECISION", "fp16"), choices=["fp32", "fp16", "bf16x3", "bf16"],
                     help="arithmetic of the head MLP GEMMs (marching/gather/compositing are fp32 in every mode)")
