@@ -446,6 +446,51 @@ class RADNeRF(nn.Module):
         return rgb
 
 
+# ------------------------------------------------------------------------------------------------ head model + super-resolution
+class RADNeRFwithSR(RADNeRF):
+    """modules/radnerfs/radnerf_sr.py:50-210: the same head field rendered at 256x256 plus the `sr_net` 256 -> 512 head
+    (genefaceplusplus_b200/superres.py).  Same extra state (`sr_net.*`, `lambda_ambient`) and result keys: `rgb_map` becomes
+    the 256x256 image [1,3,256,256], `sr_rgb_map` the clamped 512x512 one (what the driver takes when `with_sr`,
+    inference/genefacepp_infer.py:464-465, 480-481)."""
+    sr_input_resolution = 256
+
+    def __init__(self, hparams):
+        super().__init__(hparams)
+        from .superres import Superresolution
+        self.sr_net = Superresolution(channels=3)
+        self.lambda_ambient = nn.Parameter(torch.tensor([1.0]), requires_grad=False)
+
+    def render(self, rays_o, rays_d, cond, bg_coords, poses, index=0, dt_gamma=0, bg_color=None, perturb=False,
+               force_all_rays=False, max_steps=1024, T_thresh=1e-4, cond_mask=None, eye_area_percent=None, **kwargs):
+        results = super().render(rays_o, rays_d, cond, bg_coords, poses, index, dt_gamma, bg_color, perturb, force_all_rays,
+                                 max_steps, T_thresh, cond_mask, eye_area_percent=eye_area_percent, **kwargs)
+        R = self.sr_input_resolution
+        rgb_image = results["rgb_map"].reshape(1, R, R, 3).permute(0, 3, 1, 2)   # radnerf_sr.py:205 hard-codes 256 too
+        with torch.autocast(rgb_image.device.type, enabled=False):
+            sr = self.sr_net(rgb_image, noise_mode=kwargs.get("sr_noise_mode", "random")).clamp(0, 1)
+        results["rgb_map"] = rgb_image
+        results["sr_rgb_map"] = sr
+        return results
+
+    @torch.no_grad()
+    def render_clip(self, poses_c2w, intrinsics, H=256, W=256, *args, sr_noise_mode="random", sr_frames_per_call=16, **kwargs):
+        """Clip API: NeRF at 256x256 for all frames (libgfpp), then the SR head over chunks of frames.
+        Returns the clamped 512x512 frames [T,3,512,512]; `intrinsics` are those of the 256x256 camera."""
+        R = self.sr_input_resolution
+        if (H, W) != (R, R):
+            raise ValueError(f"SR models render the NeRF at {R}x{R} (radnerf_sr.py:205)")
+        want_stats = kwargs.get("want_stats", False)
+        res = super().render_clip(poses_c2w, intrinsics, H, W, *args, **kwargs)
+        rgb, stats = res if want_stats else (res, None)
+        T = rgb.shape[0]
+        out = torch.empty(T, 3, 2 * R, 2 * R, device=rgb.device, dtype=torch.float32)
+        with torch.autocast(rgb.device.type, enabled=False):
+            for s in range(0, T, sr_frames_per_call):
+                e = min(T, s + sr_frames_per_call)
+                out[s:e] = self.sr_net(rgb[s:e].view(e - s, R, R, 3).permute(0, 3, 1, 2), noise_mode=sr_noise_mode).clamp(0, 1)
+        return (out, stats) if want_stats else out
+
+
 # ------------------------------------------------------------------------------------------------ torso model
 class RADNeRFTorso(RADNeRF):
     has_torso = True

@@ -274,3 +274,36 @@ class Scene:
             "bg_coords": self.bg_coords, "poses": convert_poses(P.view(1, 4, 4)),
             "bg_color": self.bg_color, "pose4x4": P,
         }
+
+
+# ------------------------------------------------------------------------------------------------ SR head
+def hashed_uniform(n: int, salt: int, scale: float = 1.0) -> torch.Tensor:
+    """n reproducible values in [-scale/2, scale/2): an integer hash of the index, no RNG and no libm, so the golden
+    generator (which runs next to the reference) and the tests (which run anywhere) build bit-identical tensors."""
+    i = np.arange(n, dtype=np.uint64)
+    x = (i * np.uint64(2654435761) + np.uint64(salt) * np.uint64(40503)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(15)
+    x = (x * np.uint64(2246822519)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(13)
+    return torch.from_numpy(((x.astype(np.float64) / 2.0 ** 32 - 0.5) * scale).astype(np.float32))
+
+
+def synthetic_sr_state(shapes: dict, seed: int = 0) -> dict:
+    """A lively synthetic state for the SR head: `shapes` maps state_dict keys (as the module reports them) to shapes.
+    Convolution / affine weights ~U(-1,1), biases and noise strengths small but non-zero so every term of the layers is live;
+    the FIR buffers keep their constructor values (they are constants of the architecture)."""
+    out = {}
+    for n, (k, shape) in enumerate(sorted(shapes.items())):
+        if k.endswith("resample_filter"):
+            continue
+        numel = int(np.prod(shape)) if len(shape) else 1
+        if k.endswith("noise_strength"):
+            v = hashed_uniform(1, seed * 1000 + n, 0.2).reshape(())
+        elif k.endswith("affine.bias"):
+            v = 1.0 + hashed_uniform(numel, seed * 1000 + n, 0.5).reshape(shape)
+        elif k.endswith("bias"):
+            v = hashed_uniform(numel, seed * 1000 + n, 0.4).reshape(shape)
+        else:
+            v = hashed_uniform(numel, seed * 1000 + n, 2.0).reshape(shape)
+        out[k] = v
+    return out

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-3
 PSNR_MIN = 50.0
-GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith("cond_"))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if os.path.basename(p).startswith(("head", "torso")))
 
 
 def _render_both(sc, state, t, oracle_ops, max_steps=None, T_thresh=None):

@@ -158,3 +158,55 @@ def test_round_schedule_lemma(oracle_ops):
             sched.append((n_alive, n_step)); cum += n_step
             n_alive = int((D > cum).sum())
         assert sched == ref["stats"]["schedule"], (sched, ref["stats"]["schedule"])
+
+
+def test_sr_head_matches_the_reference_golden():
+    """the 256 -> 512 super-resolution head (genefaceplusplus_b200/superres.py) against the REFERENCE's
+    own Superresolution outputs (oracle/make_sr_golden.py): same state_dict keys/shapes, same numbers."""
+    import json
+    import os
+    from genefaceplusplus_b200.superres import Superresolution
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sr_head.npz"))
+    meta = json.loads(bytes(g["meta"]).decode())
+    net = Superresolution(channels=3).eval()
+    mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    ref = {k: tuple(v) for k, v in meta["shapes"].items()}
+    assert mine == ref                                                      # drop-in contract: load_state_dict(strict=True) works
+    assert (net.resample_filter - torch.from_numpy(g["resample_filter"])).abs().max().item() == 0
+    state = scn.synthetic_sr_state(ref, seed=3)
+    missing, unexpected = net.load_state_dict(state, strict=False)
+    assert not unexpected and all(k.endswith("resample_filter") for k in missing)
+    c0, c1, c2, c3 = meta["crop"]
+    small = scn.hashed_uniform(3 * 64 * 64, 77, 1.0).reshape(1, 3, 64, 64) + 0.5
+    full = scn.hashed_uniform(3 * 256 * 256, 78, 1.0).reshape(1, 3, 256, 256) + 0.5
+    with torch.no_grad():
+        for name, x in (("in64", small), ("in256", full)):
+            y = net(x, noise_mode="const")
+            assert y.shape == (1, 3, 512, 512)
+            crop = torch.from_numpy(g[f"{name}_crop"])
+            assert (y[0, :, c0:c1, c2:c3] - crop).abs().max().item() < 2e-5 * max(1.0, crop.abs().max().item()), name
+            assert np.allclose(y.double().sum(dim=(0, 2, 3)).numpy(), g[f"{name}_sum"], rtol=1e-6, atol=1e-2), name
+            assert np.allclose(y.double().abs().sum(dim=(0, 2, 3)).numpy(), g[f"{name}_abssum"], rtol=1e-6, atol=1e-2), name
+        # a batch shares the modulated kernels: identical to frame-by-frame
+        yb = net(torch.cat([full, full.flip(-1)], 0), noise_mode="const")
+        assert (yb[0] - net(full, noise_mode="const")[0]).abs().max().item() < 1e-5
+        # the noise term is live in the golden state, and 'random' differs from 'const' through it only
+        assert (net(full, noise_mode="none") - net(full, noise_mode="const")).abs().max().item() > 1e-4
+
+
+def test_sr_model_wraps_the_head_render(monkeypatch):
+    """RADNeRFwithSR (radnerf_sr.py:203-210): extra state names, result keys and shapes -- with the NeRF render stubbed out
+    (the real one needs the GPU and is covered by the head tests)."""
+    from genefaceplusplus_b200.renderer import RADNeRFwithSR
+    hp = may_hparams(add_eye_blink_cond=True, eye_blink_dim=2, with_sr=True)
+    m = RADNeRFwithSR(hp).eval()
+    keys = set(m.state_dict())
+    assert "lambda_ambient" in keys and "sr_net.block1.torgb.affine.weight" in keys and "blink_encoder.1.bias" in keys
+    fake = torch.rand(1, 256 * 256, 3)
+    monkeypatch.setattr(RADNeRF, "render", lambda self, *a, **k: {"rgb_map": fake.clone(), "depth_map": torch.zeros(1, 256 * 256)})
+    out = m.render(None, None, None, None, None, sr_noise_mode="none")
+    assert out["rgb_map"].shape == (1, 3, 256, 256) and out["sr_rgb_map"].shape == (1, 3, 512, 512)
+    assert (out["rgb_map"][0].permute(1, 2, 0).reshape(-1, 3) - fake[0]).abs().max().item() == 0
+    assert out["sr_rgb_map"].min().item() >= 0 and out["sr_rgb_map"].max().item() <= 1
+    with pytest.raises(ValueError):
+        m.render_clip(torch.eye(4)[None], may_intrinsics(512, 512), 512, 512)

@@ -14,8 +14,8 @@ import torch
 
 from genefaceplusplus_b200 import scene as scn
 
-# render fixtures only (cond_blink.npz holds conditioning vectors: tests/test_host_logic.py)
-GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith("cond_"))
+# render fixtures only (cond_blink.npz / sr_head.npz hold conditioning vectors and SR-head outputs: tests/test_host_logic.py)
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if os.path.basename(p).startswith(("head", "torso")))
 
 
 def _meta(z):
