@@ -41,8 +41,13 @@ def _mlp(x, weights, linear=None):
 
 
 class OracleModel:
-    def __init__(self, state, hparams, torso=None, fixed_order_linear=False):
-        self.st = {k: v.detach().cpu() for k, v in state.items()}
+    def __init__(self, state, hparams, torso=None, fixed_order_linear=False, backend=None, device="cpu", collect_stats=True):
+        """backend: object with the wrapper-level native-op API of oracle/ops.py (default: the C restatement on CPU;
+        oracle/gpu_ref_ops.py serves the same loop from the reference's own compiled CUDA kernels for the GPU baseline)."""
+        self.ops = backend if backend is not None else ops
+        self.dev = torch.device(device)
+        self.collect_stats = collect_stats
+        self.st = {k: v.detach().to(self.dev) for k, v in state.items()}
         self.hp = dict(hparams)
         self.torso = ("torso_embedder.embeddings" in self.st) if torso is None else torso
         self.bound = self.hp["bound"]
@@ -53,7 +58,7 @@ class OracleModel:
         self.mean_density_torso = 0  # plain attribute in the reference, not in the checkpoint (radnerf_torso.py:22)
         self.density_thresh_torso = self.hp["density_thresh_torso"]
         self.torso_shrink = self.hp["torso_shrink"]
-        self._linear = ops.linear if fixed_order_linear else None
+        self._linear = self.ops.linear if fixed_order_linear else None
         self.per_level_scale = float(np.exp2(np.log2(self.hp["desired_resolution"] * self.bound / 16) / 15))
         self.per_level_scale_amb = float(np.exp2(np.log2(self.hp["desired_resolution"] / 16) / 15))
         self.per_level_scale_torso = float(np.exp2(np.log2(2048 / 16) / 15))
@@ -72,7 +77,8 @@ class OracleModel:
         x = F.linear(x, st["cond_prenet.encoder_fc1.2.weight"], st["cond_prenet.encoder_fc1.2.bias"])  # [b, 64]
         if self.hp.get("add_eye_blink_cond", False):   # radnerf.py:97-103
             E = self.hp["eye_blink_dim"]
-            pct = torch.zeros(1, 1) if eye_area_percent is None else torch.as_tensor(eye_area_percent, dtype=torch.float32).reshape(1, 1)
+            pct = (torch.zeros(1, 1, device=x.device) if eye_area_percent is None
+                   else torch.as_tensor(eye_area_percent, dtype=torch.float32, device=x.device).reshape(1, 1))
             b = st["blink_embedding.weight"][0].reshape(1, -1) * pct
             b = F.linear(b, st["blink_encoder.0.weight"], st["blink_encoder.0.bias"])
             b = F.linear(b, st["blink_encoder.1.weight"], st["blink_encoder.1.bias"])
@@ -92,7 +98,7 @@ class OracleModel:
     # ---- field query (radnerf.py:108-141) ----
     def _grid(self, x, bound, emb, off, pls):
         x01 = (x + bound) / (2 * bound)
-        return ops.grid_encode(x01, self.st[emb], self.st[off], pls, 16, self.gridtype_id, False, self.interp_id)
+        return self.ops.grid_encode(x01, self.st[emb], self.st[off], pls, 16, self.gridtype_id, False, self.interp_id)
 
     def forward(self, position, direction, cond_feat, individual_code):
         st = self.st
@@ -107,7 +113,7 @@ class OracleModel:
         h = _mlp(h, [st[f"sigma_net.net.{i}.weight"] for i in range(self.hp["num_layers_sigma"])], self._linear)
         sigma = torch.exp(h[..., 0].float())
         geo = h[..., 1:]
-        dfeat = ops.sh_encode(direction, 4)
+        dfeat = self.ops.sh_encode(direction, 4)
         if individual_code is not None:
             cin = torch.cat([dfeat, geo, individual_code.repeat(n, 1)], dim=-1)
         else:
@@ -119,8 +125,8 @@ class OracleModel:
     def forward_torso(self, x, poses, c):
         st = self.st
         x = x * self.torso_shrink
-        enc_pose = ops.freq_encode(poses.reshape(-1, 6), 4)
-        enc_x = ops.freq_encode(x, 10)
+        enc_pose = self.ops.freq_encode(poses.reshape(-1, 6), 4)
+        enc_x = self.ops.freq_encode(x, 10)
         parts = [enc_x, enc_pose.repeat(x.shape[0], 1)]
         if c is not None:
             parts.append(c.repeat(x.shape[0], 1))
@@ -144,17 +150,18 @@ class OracleModel:
         bg_coords = bg_coords.contiguous().view(-1, 2)
         N = rays_o.shape[0]
         results = {}
-        nears, fars = ops.near_far_from_aabb(rays_o, rays_d, st["aabb_infer"], self.min_near)
+        dev = self.dev
+        nears, fars = self.ops.near_far_from_aabb(rays_o, rays_d, st["aabb_infer"], self.min_near)
         cond_feat = self.cal_cond_feat(cond)
         ind_code = st["individual_embeddings"][0] if self.hp["individual_embedding_dim"] > 0 else None
 
-        weights_sum = torch.zeros(N)
-        depth = torch.zeros(N)
-        image = torch.zeros(N, 3)
-        rays_alive = torch.arange(N, dtype=torch.int32)
+        weights_sum = torch.zeros(N, device=dev)
+        depth = torch.zeros(N, device=dev)
+        image = torch.zeros(N, 3, device=dev)
+        rays_alive = torch.arange(N, dtype=torch.int32, device=dev)
         rays_t = nears.clone()
-        knife = torch.full((N,), float("inf"))
-        n_samples = torch.zeros(N, dtype=torch.int32)
+        knife = torch.full((N,), float("inf"), device=dev)
+        n_samples = torch.zeros(N, dtype=torch.int32, device=dev)
         schedule = []
         step = 0
         S_valid = 0
@@ -164,15 +171,17 @@ class OracleModel:
                 break
             n_step = max(min(N // n_alive, 8), 1)
             schedule.append((n_alive, n_step))
-            xyzs, dirs, deltas = ops.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
+            xyzs, dirs, deltas = self.ops.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
                                                 st["density_bitfield"], self.cascade, self.grid_size, nears, fars, 128,
                                                 False, dt_gamma, max_steps)
             sigmas, rgbs, _ = self.forward(xyzs, dirs, cond_feat, ind_code)
             sigmas = self.density_scale * sigmas
-            ids = rays_alive.long().clone()  # statistics only: ray ids before composite kills them
-            ws_before = weights_sum[ids].clone()
-            ops.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh)
-            self._stats(ids, n_step, sigmas, deltas, ws_before, T_thresh, knife, n_samples)
+            if self.collect_stats:
+                ids = rays_alive.long().clone()  # statistics only: ray ids before composite kills them
+                ws_before = weights_sum[ids].clone()
+            self.ops.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh)
+            if self.collect_stats:
+                self._stats(ids, n_step, sigmas, deltas, ws_before, T_thresh, knife, n_samples)
             rays_alive = rays_alive[rays_alive >= 0]
             step += n_step
         S_valid = int(n_samples.sum().item())
@@ -185,8 +194,8 @@ class OracleModel:
             G = self.grid_size
             occ = F.grid_sample(st["density_grid_torso"].view(1, 1, G, G), bg_coords.view(1, -1, 1, 2), align_corners=True).view(-1)
             mask = occ > thr
-            torso_alpha = torch.zeros(N, 1)
-            torso_color = torch.zeros(N, 3)
+            torso_alpha = torch.zeros(N, 1, device=dev)
+            torso_color = torch.zeros(N, 3, device=dev)
             if mask.any():
                 a, c, deform = self.forward_torso(bg_coords[mask], poses, tcode)
                 torso_alpha[mask] = a.float()
@@ -217,9 +226,9 @@ class OracleModel:
         sg = sigmas[: n_alive * n_step].view(n_alive, n_step).float()
         dl = deltas[: n_alive * n_step].view(n_alive, n_step, 2)
         ws = ws_before.clone()
-        alive = torch.ones(n_alive, dtype=torch.bool)
-        row_knife = torch.full((n_alive,), float("inf"))
-        row_cnt = torch.zeros(n_alive, dtype=torch.int32)
+        alive = torch.ones(n_alive, dtype=torch.bool, device=ids.device)
+        row_knife = torch.full((n_alive,), float("inf"), device=ids.device)
+        row_cnt = torch.zeros(n_alive, dtype=torch.int32, device=ids.device)
         for k in range(n_step):
             valid = alive & (dl[:, k, 0] != 0)
             T = 1 - ws
