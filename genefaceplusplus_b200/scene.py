@@ -307,3 +307,51 @@ def synthetic_sr_state(shapes: dict, seed: int = 0) -> dict:
             v = hashed_uniform(numel, seed * 1000 + n, 2.0).reshape(shape)
         out[k] = v
     return out
+
+
+def make_torso_sr_state(hparams, seed: int = 0) -> dict:
+    """Synthetic state of the torso-SR model (modules/radnerfs/radnerf_torso_sr.py:17-61): the head + torso-grid state of
+    make_state, torso MLPs with the SR variant's input widths (freq-encoded 2-D position 42 + code 8 + freq-encoded 7 jaw
+    landmarks 126 [+ 16 head-aware features]), the head-colour encoder, the eye-blink modules and the SR head (noise
+    strengths zero, so the reference's default noise_mode='random' is deterministic)."""
+    hp = hparams
+    st = make_state(torso=True, hparams=hp, seed=seed)
+    salt = [seed * 100000 + 500]
+
+    def lin(out_f, in_f, bias=False):
+        salt[0] += 1
+        w = hashed_uniform(out_f * in_f, salt[0], 2.0 / math.sqrt(in_f)).reshape(out_f, in_f)
+        if not bias:
+            return w
+        salt[0] += 1
+        return w, hashed_uniform(out_f, salt[0], 2.0 / math.sqrt(in_f))
+
+    din = (2 + 2 * 2 * 10) + (14 + 14 * 2 * 4) + hp["torso_individual_embedding_dim"] + (16 if hp.get("torso_head_aware") else 0)
+    st["torso_deform_net.net.0.weight"] = lin(64, din)
+    st["torso_deform_net.net.1.weight"] = lin(64, 64)
+    st["torso_deform_net.net.2.weight"] = lin(2, 64)
+    st["torso_canonicial_net.net.0.weight"] = lin(32, 32 + din)
+    st["torso_canonicial_net.net.1.weight"] = lin(32, 32)
+    st["torso_canonicial_net.net.2.weight"] = lin(4, 32)
+    if hp.get("torso_head_aware"):
+        for i, (o, c) in zip((0, 2, 4), ((16, 4), (32, 16), (16, 32))):
+            st[f"head_color_weights_encoder.{i}.weight"], st[f"head_color_weights_encoder.{i}.bias"] = lin(o, c, bias=True)
+    if hp.get("add_eye_blink_cond"):
+        half = hp["cond_out_dim"] // 2
+        salt[0] += 1
+        st["blink_embedding.weight"] = hashed_uniform(half, salt[0], 1.0).reshape(1, half)
+        st["blink_encoder.0.weight"], st["blink_encoder.0.bias"] = lin(half, half, bias=True)
+        st["blink_encoder.1.weight"], st["blink_encoder.1.bias"] = lin(hp["eye_blink_dim"], half, bias=True)
+    from .superres import Superresolution
+    net = Superresolution(channels=3)
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    sr = synthetic_sr_state(shapes, seed=seed + 5)
+    for k, v in net.state_dict().items():
+        v = sr.get(k, v)
+        st["sr_net." + k] = torch.zeros_like(v) if k.endswith("noise_strength") else v.clone()
+    return st
+
+
+def lm68_sequence(T: int, salt: int = 91) -> torch.Tensor:
+    """[T, 136] synthetic 2-D landmarks in [-1, 1] (the torso-SR model reads landmarks 5..11, radnerf_torso_sr.py:84)."""
+    return hashed_uniform(T * 136, salt, 2.0).reshape(T, 136)

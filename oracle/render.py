@@ -64,6 +64,10 @@ class OracleModel:
         self.per_level_scale_torso = float(np.exp2(np.log2(2048 / 16) / 15))
         self.gridtype_id = {"tiledgrid": 1, "hashgrid": 0}[self.hp["grid_type"]]
         self.interp_id = {"linear": 0, "smoothstep": 1}[self.hp["grid_interpolation_type"]]
+        # SR variants (radnerf_sr.py / radnerf_torso_sr.py): NeRF at 256x256 + the 256 -> 512 head; the torso-SR model also
+        # swaps the torso field's inputs (jaw landmarks instead of the pose, optional head-colour features)
+        self.with_sr = bool(self.hp.get("with_sr", False)) and any(k.startswith("sr_net.") for k in self.st)
+        self._sr_net = None
 
     # ---- conditioning (radnerf.py:88-106; cond_encoder.py:98-180) ----
     def cal_cond_feat(self, cond, eye_area_percent=None):
@@ -138,10 +142,44 @@ class OracleModel:
         h = _mlp(h, [st[f"torso_canonicial_net.net.{i}.weight"] for i in range(3)], self._linear)
         return torch.sigmoid(h[..., :1]), torch.sigmoid(h[..., 1:]), dx
 
+    # ---- torso field of the SR model (radnerf_torso_sr.py:73-113) ----
+    def forward_torso_sr(self, x, poses, c, image, weights_sum, lm68):
+        st = self.st
+        x = x * self.torso_shrink
+        enc_x = self.ops.freq_encode(x, 10)
+        jaw = lm68.reshape(1, 68, 2)[:, [5, 6, 7, 8, 9, 10, 11]].reshape(1, -1)
+        enc_lm = self.ops.freq_encode(jaw.float(), 4)
+        parts = [enc_x]
+        if c is not None:
+            parts.append(c.repeat(x.shape[0], 1))
+        parts.append(enc_lm.repeat(x.shape[0], 1))
+        h = torch.cat(parts, dim=-1)
+        if self.hp.get("torso_head_aware", False):
+            e = torch.cat([image, weights_sum], dim=-1)
+            for i in (0, 2, 4):
+                e = F.linear(e, st[f"head_color_weights_encoder.{i}.weight"], st[f"head_color_weights_encoder.{i}.bias"])
+                if i != 4:
+                    e = F.leaky_relu(e, 0.02)
+            h = torch.cat([h, e], dim=-1)
+        dx = _mlp(h, [st[f"torso_deform_net.net.{i}.weight"] for i in range(3)], self._linear)
+        x = (x + dx).clamp(-1, 1).float()
+        xf = self._grid(x, 1, "torso_embedder.embeddings", "torso_embedder.offsets", self.per_level_scale_torso)
+        h = torch.cat([xf, h], dim=-1)
+        h = _mlp(h, [st[f"torso_canonicial_net.net.{i}.weight"] for i in range(3)], self._linear)
+        return torch.sigmoid(h[..., :1]), torch.sigmoid(h[..., 1:]), dx
+
+    def sr_net(self):
+        if self._sr_net is None:
+            from genefaceplusplus_b200.superres import Superresolution   # host-side torch module, itself pinned by tests/golden/sr_head.npz
+            net = Superresolution(channels=3).to(self.dev).eval()
+            net.load_state_dict({k[len("sr_net."):]: v for k, v in self.st.items() if k.startswith("sr_net.")}, strict=True)
+            self._sr_net = net
+        return self._sr_net
+
     # ---- render (renderer.py:286-399 / radnerf_torso.py:86-199), inference branch ----
     @torch.no_grad()
     def render(self, rays_o, rays_d, cond, bg_coords, poses, index=0, dt_gamma=0, bg_color=None, perturb=False,
-               force_all_rays=False, max_steps=1024, T_thresh=1e-4, **kwargs):
+               force_all_rays=False, max_steps=1024, T_thresh=1e-4, eye_area_percent=None, lm68=None, upscale_torso=False, **kwargs):
         assert not perturb
         st = self.st
         prefix = rays_o.shape[:-1]
@@ -152,7 +190,8 @@ class OracleModel:
         results = {}
         dev = self.dev
         nears, fars = self.ops.near_far_from_aabb(rays_o, rays_d, st["aabb_infer"], self.min_near)
-        cond_feat = self.cal_cond_feat(cond)
+        # renderer.py:308 and the SR classes forward eye_area_percent; the plain torso class does not (radnerf_torso.py:106)
+        cond_feat = self.cal_cond_feat(cond, eye_area_percent if (self.with_sr or not self.torso) else None)
         ind_code = st["individual_embeddings"][0] if self.hp["individual_embedding_dim"] > 0 else None
 
         weights_sum = torch.zeros(N, device=dev)
@@ -197,7 +236,10 @@ class OracleModel:
             torso_alpha = torch.zeros(N, 1, device=dev)
             torso_color = torch.zeros(N, 3, device=dev)
             if mask.any():
-                a, c, deform = self.forward_torso(bg_coords[mask], poses, tcode)
+                if self.with_sr:
+                    a, c, deform = self.forward_torso_sr(bg_coords[mask], poses, tcode, image[mask], weights_sum.unsqueeze(-1)[mask], lm68)
+                else:
+                    a, c, deform = self.forward_torso(bg_coords[mask], poses, tcode)
                 torso_alpha[mask] = a.float()
                 torso_color[mask] = c.float()
                 results["deform"] = deform
@@ -210,6 +252,16 @@ class OracleModel:
         d = torch.clamp(depth - nears, min=0) / (fars - nears)
         results["depth_map"] = d.view(*prefix)
         results["rgb_map"] = image
+        if self.with_sr:   # radnerf_sr.py:203-210, radnerf_torso_sr.py:229-246 (the 256 is hard-coded there too)
+            rgb_image = image.reshape(1, 256, 256, 3).permute(0, 3, 1, 2)
+            noise_mode = kwargs.get("sr_noise_mode", "random")
+            results["rgb_map"] = rgb_image
+            results["sr_rgb_map"] = self.sr_net()(rgb_image, noise_mode=noise_mode).clamp(0, 1)
+            if self.torso:
+                tb = results["torso_rgb_map"].reshape(1, 256, 256, 3).permute(0, 3, 1, 2)
+                results["torso_rgb_map"] = tb
+                if upscale_torso:
+                    results["sr_torso_rgb_map"] = self.sr_net()(tb, noise_mode=noise_mode).clamp(0, 1)
         # oracle-only extras
         results["weights_sum"] = weights_sum
         results["stats"] = {"S": S_valid, "schedule": schedule, "B_total": int(sum(s for _, s in schedule)),

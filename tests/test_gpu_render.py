@@ -7,6 +7,7 @@ number of torso pixels P."""
 import glob
 import json
 import os
+import re
 
 import numpy as np
 import pytest
@@ -19,7 +20,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-3
 PSNR_MIN = 50.0
-GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if os.path.basename(p).startswith(("head", "torso")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if re.match(r"(head|torso)\d+_ms", os.path.basename(p)))
 
 
 def _render_both(sc, state, t, oracle_ops, max_steps=None, T_thresh=None):

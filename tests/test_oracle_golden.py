@@ -7,6 +7,7 @@ reproduces the reference's outputs, i.e. that the oracle is pinned."""
 import glob
 import json
 import os
+import re
 
 import numpy as np
 import pytest
@@ -15,7 +16,7 @@ import torch
 from genefaceplusplus_b200 import scene as scn
 
 # render fixtures only (cond_blink.npz / sr_head.npz hold conditioning vectors and SR-head outputs: tests/test_host_logic.py)
-GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if os.path.basename(p).startswith(("head", "torso")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if re.match(r"(head|torso)\d+_ms", os.path.basename(p)))
 
 
 def _meta(z):
@@ -49,3 +50,35 @@ def test_golden_covers_plumbing_config():
     assert "head64_ms8_ds1.npz" in names
     m = _meta(np.load([p for p in GOLDEN if p.endswith("head64_ms8_ds1.npz")][0]))
     assert m["size"] == 64 and m["max_steps"] == 8 and len(m["frames"]) == 4 and not m["torso"]
+
+
+def test_oracle_torso_sr_reproduces_reference_golden(oracle_ops):
+    """the torso-SR model (jaw-landmark + head-aware torso field, eye-blink conditioning, SR head) --
+    tests/golden/torso_sr256.npz holds the REFERENCE's RADNeRFTorsowithSR.render outputs (oracle/make_torso_sr_golden.py)."""
+    from genefaceplusplus_b200.config import may_hparams
+    from oracle.render import OracleModel
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "torso_sr256.npz"))
+    m = _meta(z)
+    hp = may_hparams(**m["overrides"])
+    sc = scn.Scene(H=256, W=256, T=8, torso=True, density_scale=m["density_scale"])
+    t = m["frame"]
+    fi = sc.frame_inputs(t)
+    fi["cond"] = scn.cond_window(sc.cond, t, 3)
+    lm68 = scn.lm68_sequence(8)[t].reshape(1, 136)
+    state = scn.make_torso_sr_state(hp)
+    assert len(state) == m["n_state_keys"]
+    orc = OracleModel(state, hp)
+    orc.density_scale = m["density_scale"]
+    out = orc.render(fi["rays_o"], fi["rays_d"], fi["cond"], fi["bg_coords"], fi["poses"], index=t, bg_color=fi["bg_color"],
+                     T_thresh=sc.T_thresh, lm68=lm68, eye_area_percent=torch.tensor([[m["eye"]]]), upscale_torso=True,
+                     **{**hp, "max_steps": 16})
+    assert out["stats"]["S"] == m["stats"]["S"] and out["stats"]["P"] == m["stats"]["P"] and out["stats"]["schedule"] == [tuple(x) for x in m["stats"]["schedule"]]
+    for k, (a, b, c, d) in m["crops"].items():
+        assert (out[k][0, :, a:b, c:d] - torch.from_numpy(z[f"{k}_crop"])).abs().max().item() < 5e-6, k
+        assert np.allclose(out[k].double().sum(dim=(0, 2, 3)).numpy(), z[f"{k}_sum"], rtol=1e-6, atol=5e-2), k
+    assert abs(out["torso_alpha_map"].double().sum().item() - float(z["torso_alpha_sum"][0])) < 5e-2
+    assert abs(out["deform"].double().abs().sum().item() - float(z["deform_abssum"][0])) < 5e-2
+    # the blink and landmark inputs are live: changing them changes the image
+    out2 = orc.render(fi["rays_o"], fi["rays_d"], fi["cond"], fi["bg_coords"], fi["poses"], index=t, bg_color=fi["bg_color"],
+                      T_thresh=sc.T_thresh, lm68=-lm68, eye_area_percent=None, **{**hp, "max_steps": 16})
+    assert (out2["rgb_map"] - out["rgb_map"]).abs().max().item() > 1e-3
