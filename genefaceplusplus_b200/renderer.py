@@ -491,6 +491,160 @@ class RADNeRFwithSR(RADNeRF):
         return (out, stats) if want_stats else out
 
 
+# ------------------------------------------------------------------------------------------------ torso + super-resolution
+class _NativeEncoders:
+    """Frequency / 2-D tiled-grid encoders through libgfpp's per-op C-ABI kernels (gfpp_freq_encode_forward,
+    gfpp_grid_encode_forward): the wrapper-level API of the reference's encoders.  No CPU path."""
+
+    def __init__(self):
+        from .backend_shims import make_modules
+        mods = make_modules()
+        self._fr, self._ge = mods["_freqencoder"], mods["_gridencoder"]
+
+    def freq_encode(self, x, degree):
+        x = x.float().contiguous()
+        B, D = x.shape
+        C = D + D * 2 * degree
+        out = torch.empty(B, C, dtype=torch.float32, device=x.device)
+        if B:
+            self._fr.freq_encode_forward(x, B, D, degree, C, out)
+        return out
+
+    def grid_encode(self, x01, embeddings, offsets, per_level_scale, base_resolution, gridtype_id, align_corners, interp_id):
+        x01 = x01.float().contiguous()
+        B, D = x01.shape
+        Lv, C = offsets.shape[0] - 1, embeddings.shape[1]
+        out = torch.empty(Lv, B, C, dtype=torch.float32, device=x01.device)
+        if B:
+            self._ge.grid_encode_forward(x01, embeddings.float().contiguous(), offsets, out, B, D, C, Lv, float(np.log2(per_level_scale)),
+                                         base_resolution, None, gridtype_id, align_corners, interp_id)
+        return out.permute(1, 0, 2).reshape(B, Lv * C)
+
+
+class RADNeRFTorsowithSR(RADNeRF):
+    """modules/radnerfs/radnerf_torso_sr.py:17-246 (the `lm3d_radnerf_torso_sr.yaml` checkpoints).
+
+    Same state (`density_grid_torso`, `torso_individual_codes`, `torso_embedder.*`, `head_color_weights_encoder.*`,
+    `torso_deform_net.*`, `torso_canonicial_net.*`, `sr_net.*`, blink modules) and `render(..., lm68=, eye_area_percent=,
+    upscale_torso=)` result dict.  The head NeRF runs in libgfpp's fused kernels at 256x256; this variant's torso field --
+    2-D position (42) + code (8) + freq-encoded jaw landmarks (126) [+ a per-pixel 4->16->32->16 encoding of the head colour and
+    alpha] -> deform 64-64-2 -> tiled 2-D grid -> canonical 32-32-4 -- the three-way composite and the SR head are host-side
+    PyTorch on top of libgfpp's per-op encoder kernels for now (first correct path; the fused `k_epilogue` only knows the
+    non-SR torso field).  Pinned on CPU against tests/golden/torso_sr256.npz with the encoders injected from the checker."""
+    has_torso = False            # what gets packed for libgfpp is the head field only
+    forwards_eye_area = True     # radnerf_torso_sr.py:136
+    sr_input_resolution = 256
+
+    def __init__(self, hparams):
+        super().__init__(hparams)
+        hp = self.hparams
+        self.register_buffer("density_grid_torso", torch.zeros(self.grid_size ** 2))
+        self.mean_density_torso = 0
+        self.density_thresh_torso = hp["density_thresh_torso"]
+        self.torso_shrink = hp["torso_shrink"]
+        self.torso_individual_embedding_dim = hp["torso_individual_embedding_dim"]
+        if self.torso_individual_embedding_dim > 0:
+            self.torso_individual_codes = nn.Parameter(torch.randn(hp["individual_embedding_num"], self.torso_individual_embedding_dim) * 0.1)
+        self.torso_layout = GridLayout(2, log2_hashmap_size=16, desired_resolution=2048, gridtype="tiled")
+        self.torso_embedder = _GridParams(self.torso_layout)
+        din = (2 + 2 * 2 * 10) + (14 + 14 * 2 * 4) + self.torso_individual_embedding_dim
+        self.torso_head_aware = bool(hp["torso_head_aware"])
+        if self.torso_head_aware:
+            self.head_color_weights_encoder = nn.Sequential(nn.Linear(4, 16), nn.LeakyReLU(0.02, True), nn.Linear(16, 32),
+                                                            nn.LeakyReLU(0.02, True), nn.Linear(32, 16))
+            din += 16
+        self.torso_deform_net = _MLPWeights(din, 2, 64, 3)
+        self.torso_canonicial_net = _MLPWeights(self.torso_layout.output_dim + din, 4, 32, 3)
+        from .superres import Superresolution
+        self.sr_net = Superresolution(channels=3)
+        self.encoders = None      # _NativeEncoders on first use; tests inject the checker's CPU encoders here
+
+    @staticmethod
+    def _mlp(x, net):
+        for i, lin in enumerate(net.net):
+            x = F.linear(x, lin.weight)
+            if i != len(net.net) - 1:
+                x = F.relu(x)
+        return x
+
+    def forward_torso(self, x, poses, c=None, image=None, weights_sum=None, lm68=None):
+        """radnerf_torso_sr.py:73-113 (`poses` is accepted and unused there too)."""
+        enc = self.encoders
+        x = x * self.torso_shrink
+        enc_x = enc.freq_encode(x, 10)
+        jaw = lm68.reshape(1, 68, 2)[:, [5, 6, 7, 8, 9, 10, 11]].reshape(1, -1)
+        enc_lm = enc.freq_encode(jaw.float().to(x.device), 4)
+        parts = [enc_x] + ([c.reshape(1, -1).repeat(x.shape[0], 1)] if c is not None else []) + [enc_lm.repeat(x.shape[0], 1)]
+        h = torch.cat(parts, dim=-1)
+        if self.torso_head_aware:
+            if image is None:
+                image = torch.zeros(x.shape[0], 3, dtype=h.dtype, device=h.device)
+                weights_sum = torch.zeros(x.shape[0], 1, dtype=h.dtype, device=h.device)
+            h = torch.cat([h, self.head_color_weights_encoder(torch.cat([image, weights_sum], dim=-1))], dim=-1)
+        dx = self._mlp(h, self.torso_deform_net)
+        x = (x + dx).clamp(-1, 1).float()
+        lay = self.torso_layout
+        xf = enc.grid_encode((x + 1) / 2, self.torso_embedder.embeddings, self.torso_embedder.offsets, lay.per_level_scale,
+                             lay.base_resolution, 1, False, 0)
+        h = self._mlp(torch.cat([xf, h], dim=-1), self.torso_canonicial_net)
+        return torch.sigmoid(h[..., :1]), torch.sigmoid(h[..., 1:]), dx
+
+    def _head(self, rays_o, rays_d, cond_feat, dt_gamma, max_steps, T_thresh):
+        """Premultiplied head colour, alpha and normalised depth of one frame from libgfpp (background 0 => rgb_map == image)."""
+        N = rays_o.numel() // 3
+        res = self.render_frames(cond_feat.reshape(1, -1), rays_o=rays_o.reshape(1, -1, 3), rays_d=rays_d.reshape(1, -1, 3),
+                                 bg_color=torch.zeros(N, 3, device=self.density_bitfield.device), dt_gamma=dt_gamma,
+                                 max_steps=max_steps, T_thresh=T_thresh)
+        return res["rgb_map"].view(N, 3), res["weights_sum"].view(N), res["depth_map"].view(N)
+
+    @torch.no_grad()
+    def render(self, rays_o, rays_d, cond, bg_coords, poses, index=0, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False,
+               max_steps=1024, T_thresh=1e-4, upscale_torso=False, lm68=None, eye_area_percent=None, **kwargs):
+        if perturb:
+            raise NotImplementedError("perturb=True is a training/GUI option; the inference driver passes False")
+        if lm68 is None:
+            raise ValueError("the torso-SR field is conditioned on lm68 (radnerf_torso_sr.py:84)")
+        R = self.sr_input_resolution
+        prefix = rays_o.shape[:-1]
+        N = rays_o.numel() // 3
+        if N != R * R:
+            raise ValueError(f"SR models render the NeRF at {R}x{R} (radnerf_torso_sr.py:229)")
+        if self.encoders is None:
+            self.encoders = _NativeEncoders()
+        dev = self.density_bitfield.device
+        with torch.autocast(dev.type, enabled=False):
+            cond_feat = self.cal_cond_feat(cond.to(dev), eye_area_percent=eye_area_percent)
+            image, weights_sum, depth = self._head(rays_o.to(dev), rays_d.to(dev), cond_feat, dt_gamma, max_steps, T_thresh)
+            bg_coords = bg_coords.to(dev).contiguous().view(-1, 2)
+            bg = 1 if bg_color is None else (bg_color.to(dev).reshape(-1, 3) if torch.is_tensor(bg_color) else bg_color)
+            code = self.torso_individual_codes[0] if self.torso_individual_embedding_dim > 0 else None
+            G = self.grid_size
+            occ = F.grid_sample(self.density_grid_torso.view(1, 1, G, G), bg_coords.view(1, -1, 1, 2), align_corners=True).view(-1)
+            mask = occ > min(self.density_thresh_torso, self.mean_density_torso)
+            torso_alpha = torch.zeros(N, 1, device=dev)
+            torso_color = torch.zeros(N, 3, device=dev)
+            results = {}
+            if bool(mask.any()):
+                a, c, deform = self.forward_torso(bg_coords[mask], poses, code, image[mask] if self.torso_head_aware else None,
+                                                  weights_sum.unsqueeze(-1)[mask] if self.torso_head_aware else None, lm68=lm68)
+                torso_alpha[mask] = a.float()
+                torso_color[mask] = c.float()
+                results["deform"] = deform
+            torso_bg = torso_color * torso_alpha + bg * (1 - torso_alpha)
+            img = (image + (1 - weights_sum).unsqueeze(-1) * torso_bg).clamp(0, 1)
+            rgb_image = img.reshape(1, R, R, 3).permute(0, 3, 1, 2)
+            torso_bg = torso_bg.reshape(1, R, R, 3).permute(0, 3, 1, 2)
+            noise_mode = kwargs.get("sr_noise_mode", "random")
+            results.update({"torso_alpha_map": torso_alpha, "torso_rgb_map": torso_bg, "depth_map": depth.view(*prefix),
+                            "rgb_map": rgb_image, "sr_rgb_map": self.sr_net(rgb_image, noise_mode=noise_mode).clamp(0, 1)})
+            if upscale_torso:
+                results["sr_torso_rgb_map"] = self.sr_net(torso_bg, noise_mode=noise_mode).clamp(0, 1)
+        return results
+
+    def render_clip(self, *a, **k):
+        raise NotImplementedError("clip API of the torso-SR model: use render() per frame for now")
+
+
 # ------------------------------------------------------------------------------------------------ torso model
 class RADNeRFTorso(RADNeRF):
     has_torso = True

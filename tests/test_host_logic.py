@@ -210,3 +210,47 @@ def test_sr_model_wraps_the_head_render(monkeypatch):
     assert out["sr_rgb_map"].min().item() >= 0 and out["sr_rgb_map"].max().item() <= 1
     with pytest.raises(ValueError):
         m.render_clip(torch.eye(4)[None], may_intrinsics(512, 512), 512, 512)
+
+
+def test_torso_sr_model_host_path_matches_the_reference_golden(oracle_ops, monkeypatch):
+    """RADNeRFTorsowithSR (radnerf_torso_sr.py): torso-SR field, three-way composite and SR head of the PRODUCT class against
+    the reference's own render() outputs (tests/golden/torso_sr256.npz).  The two GPU-only pieces are stood in for by the
+    checker: the head NeRF (libgfpp's fused kernels, covered by the head tests) and the per-op encoder kernels."""
+    import json
+    import os
+    from genefaceplusplus_b200.renderer import RADNeRFTorsowithSR
+    from oracle.render import OracleModel
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "torso_sr256.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    hp = may_hparams(**meta["overrides"])
+    state = scn.make_torso_sr_state(hp)
+    m = RADNeRFTorsowithSR(hp).eval()
+    m.load_state_dict(state, strict=True)                       # the reference class loaded this very state with strict=True
+    m.density_scale = meta["density_scale"]
+    sc = scn.Scene(H=256, W=256, T=8, torso=True, density_scale=meta["density_scale"])
+    t = meta["frame"]
+    fi = sc.frame_inputs(t)
+    cond = scn.cond_window(sc.cond, t, 3)
+    lm68 = scn.lm68_sequence(8)[t].reshape(1, 136)
+    eye = torch.tensor([[meta["eye"]]])
+    head = OracleModel(state, {**hp, "with_sr": False}, torso=False)
+    head.density_scale = meta["density_scale"]
+
+    def fake_head(self, rays_o, rays_d, cond_feat, dt_gamma, max_steps, T_thresh):
+        assert (cond_feat.reshape(-1) - head.cal_cond_feat(cond, eye).reshape(-1)).abs().max().item() < 1e-6     # product cond nets, blink incl.
+        r = head.render(rays_o.view(1, -1, 3), rays_d.view(1, -1, 3), cond, fi["bg_coords"], fi["poses"], bg_color=torch.zeros(256 * 256, 3),
+                        T_thresh=T_thresh, eye_area_percent=eye, **{**hp, "with_sr": False, "max_steps": max_steps, "dt_gamma": dt_gamma})
+        return r["rgb_map"].view(-1, 3), r["weights_sum"].view(-1), r["depth_map"].view(-1)
+
+    monkeypatch.setattr(RADNeRFTorsowithSR, "_head", fake_head)
+    m.encoders = oracle_ops
+    kw = {k: v for k, v in hp.items() if k not in ("max_steps", "dt_gamma", "bg_color")}
+    out = m.render(fi["rays_o"], fi["rays_d"], cond, fi["bg_coords"], fi["poses"], index=t, dt_gamma=hp["dt_gamma"], bg_color=fi["bg_color"],
+                   max_steps=16, T_thresh=sc.T_thresh, upscale_torso=True, lm68=lm68, eye_area_percent=eye, staged=False, **kw)
+    assert out["rgb_map"].shape == (1, 3, 256, 256) and out["sr_rgb_map"].shape == (1, 3, 512, 512) and out["sr_torso_rgb_map"].shape == (1, 3, 512, 512)
+    for k, (a, b, c, d) in meta["crops"].items():
+        assert (out[k][0, :, a:b, c:d] - torch.from_numpy(z[f"{k}_crop"])).abs().max().item() < 5e-6, k
+    assert abs(out["torso_alpha_map"].double().sum().item() - float(z["torso_alpha_sum"][0])) < 5e-2
+    assert abs(out["deform"].double().abs().sum().item() - float(z["deform_abssum"][0])) < 5e-2
+    with pytest.raises(ValueError):
+        m.render(fi["rays_o"], fi["rays_d"], cond, fi["bg_coords"], fi["poses"], lm68=None)
