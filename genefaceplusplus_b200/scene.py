@@ -355,3 +355,13 @@ def make_torso_sr_state(hparams, seed: int = 0) -> dict:
 def lm68_sequence(T: int, salt: int = 91) -> torch.Tensor:
     """[T, 136] synthetic 2-D landmarks in [-1, 1] (the torso-SR model reads landmarks 5..11, radnerf_torso_sr.py:84)."""
     return hashed_uniform(T * 136, salt, 2.0).reshape(T, 136)
+
+
+def make_head_sr_state(hparams, seed: int = 0) -> dict:
+    """Synthetic state of the head-SR model (modules/radnerfs/radnerf_sr.py:50-115): make_state's head + blink modules + SR head
+    (noise strengths zero) + `lambda_ambient`."""
+    full = make_torso_sr_state({**hparams, "torso_head_aware": False}, seed=seed)
+    drop = ("torso_", "density_grid_torso", "head_color_weights_encoder.")
+    st = {k: v for k, v in full.items() if not k.startswith(drop)}
+    st["lambda_ambient"] = torch.tensor([1.0])
+    return st

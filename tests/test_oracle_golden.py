@@ -82,3 +82,46 @@ def test_oracle_torso_sr_reproduces_reference_golden(oracle_ops):
     out2 = orc.render(fi["rays_o"], fi["rays_d"], fi["cond"], fi["bg_coords"], fi["poses"], index=t, bg_color=fi["bg_color"],
                       T_thresh=sc.T_thresh, lm68=-lm68, eye_area_percent=None, **{**hp, "max_steps": 16})
     assert (out2["rgb_map"] - out["rgb_map"]).abs().max().item() > 1e-3
+
+
+def test_head_sr_oracle_and_product_reproduce_reference_golden(oracle_ops, monkeypatch):
+    """RADNeRFwithSR (radnerf_sr.py:203-210): tests/golden/head_sr256.npz holds the reference's own render() outputs
+    (oracle/make_head_sr_golden.py).  Checked: the oracle's head-SR path, and the product class with its NeRF render (libgfpp,
+    GPU-only, covered elsewhere) stood in for by the oracle."""
+    from genefaceplusplus_b200.config import may_hparams
+    from genefaceplusplus_b200.renderer import RADNeRF, RADNeRFwithSR
+    from oracle.render import OracleModel
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "head_sr256.npz"))
+    m = _meta(z)
+    hp = may_hparams(**m["overrides"])
+    sc = scn.Scene(H=256, W=256, T=8, torso=False, density_scale=m["density_scale"])
+    t = m["frame"]
+    fi = sc.frame_inputs(t)
+    fi["cond"] = scn.cond_window(sc.cond, t, 3)
+    state = scn.make_head_sr_state(hp)
+    assert len(state) == m["n_state_keys"]
+    eye = torch.tensor([[m["eye"]]])
+    orc = OracleModel(state, hp)
+    orc.density_scale = m["density_scale"]
+    kw = dict(index=t, bg_color=fi["bg_color"], T_thresh=sc.T_thresh, eye_area_percent=eye)
+    out = orc.render(fi["rays_o"], fi["rays_d"], fi["cond"], fi["bg_coords"], fi["poses"], **kw, **{**hp, "max_steps": 16})
+    assert out["stats"]["S"] == m["stats"]["S"]
+    for k, (a, b, c, d) in m["crops"].items():
+        assert (out[k][0, :, a:b, c:d] - torch.from_numpy(z[f"{k}_crop"])).abs().max().item() < 5e-6, k
+        assert np.allclose(out[k].double().sum(dim=(0, 2, 3)).numpy(), z[f"{k}_sum"], rtol=1e-6, atol=5e-2), k
+    # product class: same state with strict=True; render() = parent's NeRF render + SR head
+    prod = RADNeRFwithSR(hp).eval()
+    prod.load_state_dict(state, strict=True)
+    plain = OracleModel(state, {**hp, "with_sr": False}, torso=False)
+    plain.density_scale = m["density_scale"]
+
+    def fake_render(self, rays_o, rays_d, cond, bg_coords, poses, *a, eye_area_percent=None, **k):
+        assert eye_area_percent is not None                      # renderer.py:308: the head classes forward it
+        r = plain.render(rays_o, rays_d, cond, bg_coords, poses, bg_color=fi["bg_color"], T_thresh=sc.T_thresh,
+                         eye_area_percent=eye_area_percent, **{**hp, "with_sr": False, "max_steps": 16})
+        return {"rgb_map": r["rgb_map"], "depth_map": r["depth_map"]}
+
+    monkeypatch.setattr(RADNeRF, "render", fake_render)
+    res = prod.render(fi["rays_o"], fi["rays_d"], fi["cond"], fi["bg_coords"], fi["poses"], eye_area_percent=eye)
+    for k, (a, b, c, d) in m["crops"].items():
+        assert (res[k][0, :, a:b, c:d] - torch.from_numpy(z[f"{k}_crop"])).abs().max().item() < 5e-6, k
