@@ -557,7 +557,8 @@ class RADNeRFTorsowithSR(RADNeRF):
         self.torso_canonicial_net = _MLPWeights(self.torso_layout.output_dim + din, 4, 32, 3)
         from .superres import Superresolution
         self.sr_net = Superresolution(channels=3)
-        self.encoders = None      # _NativeEncoders on first use; tests inject the checker's CPU encoders here
+        self.encoders = None      # _NativeEncoders (libgfpp per-op kernels) on first use.  Nothing in the package sets this: it is the
+                                  # seam through which the CPU unit test of the host logic supplies the checker's encoders
 
     @staticmethod
     def _mlp(x, net):
@@ -641,8 +642,30 @@ class RADNeRFTorsowithSR(RADNeRF):
                 results["sr_torso_rgb_map"] = self.sr_net(torso_bg, noise_mode=noise_mode).clamp(0, 1)
         return results
 
-    def render_clip(self, *a, **k):
-        raise NotImplementedError("clip API of the torso-SR model: use render() per frame for now")
+    @torch.no_grad()
+    def render_clip(self, poses_c2w, intrinsics, H=256, W=256, cond_seq=None, bg_color=None, bg_coords=None, lm68_seq=None,
+                    eye_area_percent=None, dt_gamma=None, max_steps=None, T_thresh=1e-2, sr_noise_mode="random", **unused):
+        """Clip convenience for the torso-SR model: frame-by-frame `render()` (the torso field of this variant is still
+        host-side), returning the clamped 512x512 frames [T,3,512,512].  poses_c2w [T,4,4] (c2w, dataset.poses), cond_seq
+        [T,1,C], lm68_seq [T,136], eye_area_percent [T] or None."""
+        from .scene import cond_window, convert_poses, get_rays
+        R = self.sr_input_resolution
+        if (H, W) != (R, R):
+            raise ValueError(f"SR models render the NeRF at {R}x{R} (radnerf_torso_sr.py:229)")
+        hp = self.hparams
+        T = poses_c2w.shape[0]
+        dev = self.density_bitfield.device
+        out = torch.empty(T, 3, 2 * R, 2 * R, device=dev, dtype=torch.float32)
+        for t in range(T):
+            rays_o, rays_d = get_rays(poses_c2w[t].cpu(), intrinsics, H, W)
+            res = self.render(rays_o.to(dev), rays_d.to(dev), cond_window(cond_seq, t, self.smo_win_size).to(dev), bg_coords,
+                              convert_poses(poses_c2w[t].cpu().view(1, 4, 4)).to(dev), index=t,
+                              dt_gamma=hp["dt_gamma"] if dt_gamma is None else dt_gamma, bg_color=bg_color,
+                              max_steps=hp["max_steps"] if max_steps is None else max_steps, T_thresh=T_thresh, lm68=lm68_seq[t].reshape(1, -1),
+                              eye_area_percent=None if eye_area_percent is None else eye_area_percent[t].reshape(1, 1),
+                              sr_noise_mode=sr_noise_mode)
+            out[t] = res["sr_rgb_map"][0]
+        return out
 
 
 # ------------------------------------------------------------------------------------------------ torso model
