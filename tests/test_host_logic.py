@@ -254,3 +254,37 @@ def test_torso_sr_model_host_path_matches_the_reference_golden(oracle_ops, monke
     assert abs(out["deform"].double().abs().sum().item() - float(z["deform_abssum"][0])) < 5e-2
     with pytest.raises(ValueError):
         m.render(fi["rays_o"], fi["rays_d"], cond, fi["bg_coords"], fi["poses"], lm68=None)
+
+
+def test_driver_shim_conditioning_and_plumbing():
+    """genefaceplusplus_b200/driver.py: batched conditioning == per-frame cal_cond_feat on the driver's own
+    window lists; the render loop hands libgfpp the right chunks (render_frames stubbed: it needs the GPU)."""
+    from genefaceplusplus_b200 import driver
+    hp = may_hparams(add_eye_blink_cond=True, eye_blink_dim=2)
+    sc = scn.Scene(H=8, W=8, T=7, torso=True)
+    m = RADNeRFTorso(hp).eval()
+    m.load_state_dict(sc.state, strict=False)
+    head = RADNeRF(hp).eval()
+    head.load_state_dict({k: v for k, v in sc.state.items() if not k.startswith(("torso_", "density_grid_torso"))}, strict=False)
+    wins = [scn.cond_window(sc.cond, t) for t in range(7)]
+    eye = [torch.tensor([[0.1 * t]]) for t in range(7)]
+    with torch.no_grad():
+        f_head = driver.cond_feat_from_windows(head, wins, eye)
+        f_torso = driver.cond_feat_from_windows(m, wins, eye)
+        for t in range(7):
+            assert (f_head[t] - head.cal_cond_feat(wins[t], eye_area_percent=eye[t])).abs().max().item() < 1e-6
+            assert (f_torso[t] - m.cal_cond_feat(wins[t])).abs().max().item() < 1e-6       # radnerf_torso.py:106: no eye input
+    calls = []
+
+    def fake_render_frames(cond_feat, **kw):
+        calls.append((cond_feat.shape[0], tuple(kw["rays_o"].shape), tuple(kw["pose6"].shape)))
+        return {"rgb_map": torch.full((cond_feat.shape[0], 64, 3), 0.5)}
+
+    m.render_frames = fake_render_frames
+    fis = [sc.frame_inputs(t) for t in range(7)]
+    batch = {"rays_o": [f["rays_o"] for f in fis], "rays_d": [f["rays_d"] for f in fis], "cond_wins": wins, "poses": [f["poses"] for f in fis],
+             "bg_coords": sc.bg_coords, "bg_img": sc.bg_color, "eye_area_percent": eye}
+    out = driver.render_driver_batch(m, batch, frames_per_call=3)
+    assert out.shape == (7, 3, 8, 8) and calls == [(3, (3, 64, 3), (3, 6)), (3, (3, 64, 3), (3, 6)), (1, (1, 64, 3), (1, 6))]
+    u8 = driver.video_uint8(out)
+    assert u8.dtype == torch.uint8 and u8.shape == (7, 8, 8, 3) and int(u8[0, 0, 0, 0]) == 127
