@@ -288,3 +288,15 @@ def test_driver_shim_conditioning_and_plumbing():
     assert out.shape == (7, 3, 8, 8) and calls == [(3, (3, 64, 3), (3, 6)), (3, (3, 64, 3), (3, 6)), (1, (1, 64, 3), (1, 6))]
     u8 = driver.video_uint8(out)
     assert u8.dtype == torch.uint8 and u8.shape == (7, 8, 8, 3) and int(u8[0, 0, 0, 0]) == 127
+
+
+def test_sr_model_clip_api(monkeypatch):
+    """RADNeRFwithSR.render_clip: NeRF clip at 256x256 (stubbed: GPU) -> SR head in chunks -> [T,3,512,512] in [0,1]."""
+    from genefaceplusplus_b200.renderer import RADNeRFwithSR
+    m = RADNeRFwithSR(may_hparams(with_sr=True)).eval()
+    fake = torch.rand(5, 256 * 256, 3)
+    monkeypatch.setattr(RADNeRF, "render_clip", lambda self, *a, **k: fake.clone())
+    out = m.render_clip(torch.eye(4).repeat(5, 1, 1), may_intrinsics(256, 256), 256, 256, sr_noise_mode="none", sr_frames_per_call=2)
+    assert out.shape == (5, 3, 512, 512) and 0 <= out.min().item() and out.max().item() <= 1
+    one = m.sr_net(fake[3].view(1, 256, 256, 3).permute(0, 3, 1, 2), noise_mode="none").clamp(0, 1)
+    assert (out[3] - one[0]).abs().max().item() < 1e-5          # chunking does not change a frame
