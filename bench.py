@@ -22,6 +22,7 @@ Timed numbers:
 import argparse
 import ctypes
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -46,7 +47,8 @@ def parse():
     ap.add_argument("--frames-per-call", type=int, default=50)
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the bounded CPU-baseline sample (~3.5 s each on the box)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default=os.environ.get("GFPP_BENCH_PRECISION", "fp16"), choices=["fp32", "fp16", "bf16x3", "bf16"],
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own CUDA kernels (oracle/_ref) beside ours")
+    ap.add_argument("--precision", default=os.environ.get("GFPP_BENCH_PRECISION", DEFAULT_PRECISION), choices=["fp32", "fp16", "bf16x3", "bf16", "robust"],
                     help="arithmetic of the head MLP GEMMs (marching/gather/compositing are fp32 in every mode)")
     return ap.parse_args()
 
@@ -108,9 +110,16 @@ class ClockSampler:
 
 
 _CPU_THREADS = None
+DEFAULT_PRECISION = "fp16"                 # the headline mode of this bench
+SMOKE_PRECISIONS = ("fp16",)               # what __graft_entry__.smoke() renders beside the fp32 kernels
 
 
-def cpu_reference_fps(args, n_frames):
+def metric_name(args):
+    """ONE metric string for both arms (the driver pairs the two JSON lines by it)."""
+    return f"frames/sec at {args.size}x{args.size} " + ("head" if args.head_only else "head+torso")
+
+
+def cpu_reference_fps(args, n_frames, keep_images=False):
     """The reference's path on the host cores: the reference's PyTorch-eager modules restated in oracle/render.py
     over the C restatement of its CUDA-only native ops (kind "port": the reference has no CPU implementation of
     those ops and its Python cannot travel to the GPU box).  All host threads."""
@@ -142,12 +151,17 @@ def cpu_reference_fps(args, n_frames):
     torch.set_num_threads(cores); ops.set_num_threads(cores)
     t0 = time.time()
     S = 0
+    imgs, knife = [], []
     for t in range(n_frames):
         fi = sc.frame_inputs(t)
         out = orc.render(fi["rays_o"], fi["rays_d"], fi["cond"], fi["bg_coords"], fi["poses"], bg_color=fi["bg_color"],
                          T_thresh=sc.T_thresh, **sc.hparams)
         S += out["stats"]["S"]
+        if keep_images:
+            imgs.append(out["rgb_map"].reshape(-1, 3).clone()); knife.append(out["knife"].reshape(-1).clone())
     dt = time.time() - t0
+    if keep_images:
+        return n_frames / dt, cores, dt, S, torch.stack(imgs), torch.stack(knife)
     return n_frames / dt, cores, dt, S
 
 
@@ -169,12 +183,14 @@ def run_reference(args, out=sys.stdout):
         fps, cores, dt, _ = cpu_reference_fps(args, args.cpu_frames)
         fps_list.append(fps); t_total += dt
     v = args.cpu_frames * args.steps / t_total
-    line = {"impl": "reference", "metric": "frames/sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": metric_name(args), "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "sample": f"{args.cpu_frames} frame(s) of the clip per step"},
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.cpu_frames} frame(s) at {args.size}x{args.size} per step, {args.steps} steps"},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{args.cpu_frames} frame(s) at {args.size}x{args.size} per step, {args.steps} steps",
+                             "note": "oracle/render.py + oracle/native_ops.c (CPU restatement of the reference path; the reference's own Python "
+                                     "has no CPU implementation of its native ops and does not travel to this box); `cores` = calibrated thread count"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=out)
 
@@ -235,7 +251,8 @@ def _main(args, out):
     cond_dev = cond_host.to(dev)
     N = H * W
     rgb = torch.empty(T, N, 3, device=dev, dtype=torch.float32)
-    u8_host = torch.empty(T, N, 3, dtype=torch.uint8).pin_memory()
+    u8 = torch.empty(T, N, 3, device=dev, dtype=torch.uint8)
+    u8_host = torch.empty(T * world if rank == 0 else 1, N, 3, dtype=torch.uint8).pin_memory()
     launches = 0
 
     def step_device():
@@ -244,26 +261,34 @@ def _main(args, out):
         n0 = 0
         for a in range(0, T, args.frames_per_call):
             b = min(T, a + args.frames_per_call)
+            # frames land in the clip buffer straight from the epilogue kernel: fp32 at N=1, the uint8 video frames at N>1
+            # (what the all-gather moves)
             res = model.render_frames(feat[a:b], poses_c2w=poses_dev[a:b], intrinsics=sc.intrinsics, H=H, W=W,
                                       pose6=pose6_dev[a:b] if not args.head_only else None, bg_coords=bg_coords, bg_color=bg_color,
                                       dt_gamma=sc.hparams["dt_gamma"], max_steps=sc.hparams["max_steps"], T_thresh=sc.T_thresh,
-                                      want_torso_maps=False, want_stats=True)
-            rgb[a:b].copy_(res["rgb_map"])
+                                      want_torso_maps=False, want_stats=True, want_aux=False,
+                                      **({"u8_out": u8[a:b]} if world > 1 else {"rgb_out": rgb[a:b]}))
             stats_acc.append(res["stats"])
             n0 += model.last_launch_count
         launches += n0
         if world > 1:
-            return gdist.gather_frames(gdist.to_uint8(rgb), T * world)
+            return gdist.gather_frames(u8, T * world)
         return rgb
 
     def step_e2e():
+        """The call a user makes, from HOST buffers: H2D of this rank's poses + the conditioning sequence, euler/translation
+        conversion of the poses, conditioning nets, render (uint8 frames written by the epilogue kernel), at N>1 the all-gather of
+        the uint8 clip, and the D2H of the finished clip (whole clip on rank 0)."""
         p = poses_host.to(dev, non_blocking=True)
         c = cond_host.to(dev, non_blocking=True)
-        out = model.render_clip(p, sc.intrinsics, H, W, cond_seq=c, bg_color=bg_color, bg_coords=bg_coords, pose6=pose6_dev,
-                                T_thresh=sc.T_thresh, frames_per_call=args.frames_per_call, out=rgb)
-        cf = None
-        u8_host.copy_(gdist.to_uint8(out), non_blocking=True)
-        return cf
+        p6 = scn.convert_poses(poses_host).to(dev, non_blocking=True) if not args.head_only else None
+        cf = model.cal_cond_feat_clip(c)[s:e]
+        out = model.render_clip(p, sc.intrinsics, H, W, cond_feat=cf, bg_color=bg_color, bg_coords=bg_coords, pose6=p6,
+                                T_thresh=sc.T_thresh, frames_per_call=args.frames_per_call, out=u8, as_uint8=True)
+        if world > 1:
+            out = gdist.gather_frames(out, T * world)
+        if rank == 0:
+            u8_host.copy_(out, non_blocking=True)
 
     pose6_dev = scn.convert_poses(poses_host).to(dev) if not args.head_only else None
     stats_acc = []
@@ -314,23 +339,41 @@ def _main(args, out):
         if it >= 2:
             head_ms.append(buf[0]); pass2_ms.append(buf[1]); epi_ms.append(buf[2]); pre_ms.append(buf[3])
     L.gfpp_profile_enable(0)
-    hbm, peak_kind, _ = peaks()
+    hbm, peak_kind, pk = peaks()
     head_t = statistics.mean(head_ms) / 1000.0
     # 2 grids x 16 levels x 8 corners x 8 B per valid sample; per ray 12 B colour + 4 B alpha + 4 B depth out
     # (+24 B when rays are supplied: here they are generated in-kernel); + the packed weights once
     alg_bytes = Fc * (S_per_frame * 2048 + N * (12 + 4 + 4)) + 0.36e6
     alg_flops = Fc * S_per_frame * 178944
     achieved = alg_bytes / head_t / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tp) and args.precision == "fp16":
-        traffic = json.load(open(tp))["dram_bytes_per_frame"] * Fc     # from one ncu --set full capture, scaled to this launch size
-    roofline = {"bound": "hbm", "kernel": "k_head (pass 1)" if args.precision == "fp32" else "k_head_tc (pass 1)", "achieved": achieved, "peak": hbm, "peak_source": peak_kind, "unit": "GB/s",
-                "frac": achieved / hbm, "traffic": traffic, "launch_ms": head_t * 1000.0, "frames_per_launch": Fc,
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if args.precision in tj:
+            traffic = tj[args.precision]["dram_bytes_per_frame"] * Fc
+            traffic_src = "static: " + tj[args.precision]["source"] + " (not measured in this run; scaled to this launch size)"
+    # what physically moves: the fp16 / int16 'oct' layouts hold the 8 corners of a cell in ONE 32-byte sector per (sample, level),
+    # the fp32 'quad' layout in two; everything is L2-resident, so the binding resources are L1/L2 sector rate and the tensor pipe
+    sectors_per_sample = 2 * 16 * (1 if args.precision in ("fp16", "robust") else 2)
+    sm_hz = 1e6 * (clocks.get("sm_mhz") or 1965.0) if rank == 0 else 1.965e9
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    sector_rate = Fc * S_per_frame * sectors_per_sample / head_t          # sectors / s
+    bf16_peak = (pk.get("bf16_tflops_sustained") or 1460.6)
+    kname = {"fp32": "k_head (pass 1)", "bf16": "k_head_tc (pass 1)", "bf16x3": "k_head_tc (pass 1)"}.get(args.precision, "k_head_v2 (pass 1)")
+    if os.environ.get("GFPP_HEAD_V1"):
+        kname = "k_head_tc (pass 1)"
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm, "peak_source": peak_kind, "unit": "GB/s",
+                "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src, "launch_ms": head_t * 1000.0, "frames_per_launch": Fc,
                 "share_of_step": head_t / (head_t + (statistics.mean(pass2_ms) + statistics.mean(epi_ms) + statistics.mean(pre_ms)) / 1000),
                 "ray_setup_ms": statistics.mean(pre_ms),
                 "fp32_tflops": alg_flops / head_t / 1e12, "pass2_ms": statistics.mean(pass2_ms), "epilogue_ms": statistics.mean(epi_ms),
-                "alg_bytes_per_frame": alg_bytes / Fc, "alg_flops_per_frame": alg_flops / Fc}
+                "alg_bytes_per_frame": alg_bytes / Fc, "alg_flops_per_frame": alg_flops / Fc,
+                "gathered_bytes_per_frame": S_per_frame * sectors_per_sample * 32,
+                "l2_sector_frac": sector_rate / (1.0 * n_sm * sm_hz),
+                "l2_sector_note": "scattered 32-byte sectors per second / (1.0 sector per clock per SM: the measured ceiling, profiles/microbench_gather_r01.txt)",
+                "tensor_frac": alg_flops / head_t / 1e12 / bf16_peak,
+                "tensor_note": "algorithmic MLP flops per second / measured sustained dense bf16 peak (MEASURED_PEAKS.json)"}
 
     # ---------------- end to end (host buffers in, uint8 frames out) ----------------
     for _ in range(2):
@@ -346,17 +389,48 @@ def _main(args, out):
     if world > 1:
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e2e_fps = world * T * args.steps / (ems.item() / 1000.0)
-    h2d = poses_host.numel() * 4 + cond_host.numel() * 4
+    h2d = poses_host.numel() * 4 + cond_host.numel() * 4 + (0 if args.head_only else T * 6 * 4)
     d2h = u8_host.numel()
 
     cpu = None
+    parity = None
     if rank == 0 and not args.no_cpu_baseline:
-        v, cores, dt, _ = cpu_reference_fps(args, args.cpu_frames)
-        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_frames} frame(s) of the same clip at {H}x{W} ({dt:.1f} s)"}
+        v, cores, dt, _, ref_img, ref_knife = cpu_reference_fps(args, args.cpu_frames, keep_images=True)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "port",
+               "sample": f"{args.cpu_frames} frame(s) of the same clip at {H}x{W} ({dt:.1f} s)",
+               "note": "oracle/render.py + oracle/native_ops.c on the host cores (the reference's Python has no CPU path for its native ops "
+                       "and does not travel to this box); `cores` = calibrated thread count, `host_cores` = os.cpu_count()"}
+        # parity of the BENCHMARKED configuration: the same frames through the timed path (clip API, in-kernel rays, timed
+        # precision) against the fp32 CPU oracle's frames just rendered for the baseline (max-abs 1e-3 / PSNR 50 dB)
+        Fp = args.cpu_frames
+        mine = model.render_clip(poses_dev[:Fp], sc.intrinsics, H, W, cond_feat=model.cal_cond_feat_clip(cond_dev)[s:s + Fp],
+                                 bg_color=bg_color, bg_coords=bg_coords, pose6=pose6_dev[:Fp] if not args.head_only else None,
+                                 T_thresh=sc.T_thresh, frames_per_call=args.frames_per_call).float().cpu()
+        d = (mine - ref_img).abs().max(-1).values                       # [F,N]
+        knife = ref_knife < 1e-3                                         # rays whose termination an fp32 reordering may flip
+        mse = ((mine.double() - ref_img.double()) ** 2).mean().item()
+        parity = {"vs": "fp32 CPU oracle (oracle/render.py), identical poses / conditioning; rays generated in-kernel vs torch get_rays",
+                  "precision": args.precision, "frames": Fp, "size": H,
+                  "max_abs": d[~knife].max().item(), "max_abs_all": d.max().item(), "n_knife": int(knife.sum()),
+                  "n_over_1e-3": int((d > 1e-3).sum()), "n_pixels": d.numel(),
+                  "psnr": 999.0 if mse == 0 else 10 * math.log10(1.0 / mse), "tolerance": {"max_abs": 1e-3, "psnr": 50.0}}
+        parity["ok"] = bool(parity["max_abs"] <= 1e-3 and parity["psnr"] >= 50.0)
+    gpu_ref = None
+    if rank == 0 and not args.no_gpu_reference:
+        # the reference's own CUDA kernels (oracle/_ref, built unmodified) under its host loop, same box, same run
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import ref_gpu_baseline
+            if ref_gpu_baseline.available():
+                precs = ("fp32", args.precision) if args.precision != "fp32" else ("fp32",)
+                gpu_ref = ref_gpu_baseline.measure(H, 8, args.density_scale, precisions=precs, torso=not args.head_only)
+            else:
+                gpu_ref = {"unavailable": "oracle/_ref/*.so not present (they are built where /root/reference exists and travel with the repo)"}
+        except Exception as ex:   # a baseline measurement must never take the bench down
+            gpu_ref = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
 
     if rank == 0:
-        line = {"metric": "frames/sec at 512x512 head+torso" if not args.head_only else "frames/sec at 512x512 head", "value": fps,
+        line = {"metric": metric_name(args), "value": fps,
                 "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fp32": "f32", "fp16": "f16 operands, f32 accumulate (tcgen05)", "bf16x3": "bf16 hi/lo split x3, f32 accumulate (tcgen05)", "bf16": "bf16 operands, f32 accumulate (tcgen05)"}[args.precision],
@@ -366,8 +440,10 @@ def _main(args, out):
                            "parallelism": f"frame-sharded x{world}, 1 all-gather of uint8 RGB" if world > 1 else "single GPU",
                            "l2": "per-step working set (786 MB fp32 frames out + 1.8 GB workspace) >> 126 MB L2; grid tables (14.4 MB) are L2-resident by design"},
                 "clocks": clocks, "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                          "note": "pinned host poses+conditioning in, uint8 [T,H,W,3] frames out"},
-                "gpu_launches": timed_launches, "roofline": roofline, "cpu_baseline": cpu}
+                                          "note": "pinned host poses+conditioning in (H2D, pose conversion and conditioning nets inside the timed "
+                                                  "region), uint8 [T,H,W,3] frames written by the epilogue kernel" +
+                                                  (", all-gather of the uint8 clip, D2H of the whole clip on rank 0" if world > 1 else ", D2H of the clip")},
+                "gpu_launches": timed_launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "gpu_reference": gpu_ref}
         print(json.dumps(line), file=out)
     if world > 1:
         dist.destroy_process_group()

@@ -16,8 +16,32 @@ import torch
 from . import _capi
 
 
-def _P(t):
+def _P(t, dtype=None):
+    """Device pointer with the checks the reference's pybind layer makes (CHECK_CUDA / CHECK_CONTIGUOUS / dtype): a CPU, strided
+    or wrongly typed tensor raises RuntimeError here instead of faulting asynchronously inside a kernel."""
+    if not torch.is_tensor(t) or not t.is_cuda:
+        raise RuntimeError("libgfpp: expected a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError("libgfpp: expected a contiguous tensor")
+    want = dtype if dtype is not None else _DTYPES.get(t.dtype)
+    if want is None or t.dtype != want:
+        raise RuntimeError(f"libgfpp: unsupported dtype {t.dtype} (fp32 / int32 / uint8 buffers only; run the encoders with autocast disabled)")
     return ctypes.c_void_p(t.data_ptr())
+
+
+_DTYPES = {torch.float32: torch.float32, torch.int32: torch.int32, torch.uint8: torch.uint8}
+_OFFSETS_HOST = {}
+
+
+def _offsets_host(offsets):
+    """Host copy of a grid's level offsets, cached by (data_ptr, numel, version): no D2H sync per encoder call."""
+    key = (offsets.data_ptr(), offsets.numel(), int(offsets._version))
+    off = _OFFSETS_HOST.get(key)
+    if off is None:
+        if len(_OFFSETS_HOST) > 64:
+            _OFFSETS_HOST.clear()
+        off = _OFFSETS_HOST[key] = np.ascontiguousarray(offsets.detach().cpu().numpy().astype(np.int32))
+    return off
 
 
 def _ck(rc, what):
@@ -57,8 +81,8 @@ def make_modules():
             raise NotImplementedError("grid_encode_forward with dy_dx is a training path")
         if emb.dtype != torch.float32:
             raise RuntimeError("libgfpp grid tables are fp32 (run the encoder with autocast disabled)")
-        off = np.ascontiguousarray(offsets.detach().cpu().numpy().astype(np.int32))
-        _ck(L.gfpp_grid_encode_forward(_P(inputs), _P(emb), off.ctypes.data_as(ctypes.c_void_p), _P(outputs), B, D, C, Lv, cf(S_), H, gridtype,
+        off = _offsets_host(offsets)
+        _ck(L.gfpp_grid_encode_forward(_P(inputs, torch.float32), _P(emb), off.ctypes.data_as(ctypes.c_void_p), _P(outputs, torch.float32), B, D, C, Lv, cf(S_), H, gridtype,
                                        int(align_corners), interp, S()), "grid_encode_forward")
 
     ge.grid_encode_forward = grid_encode_forward

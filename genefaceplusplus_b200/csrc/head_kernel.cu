@@ -438,12 +438,9 @@ __global__ void k_schedule(const int *__restrict__ hist, int n_frames, int n_ray
 size_t head_smem_bytes() { return sizeof(Smem); }
 
 cudaError_t launch_head(const HeadArgs &a, int total_hint, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // function attributes are per device: set on every launch, never cached process-wide
+    cudaError_t e = cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
     int blocks = sm_count();
     if (total_hint >= 0) {
         const int need = (total_hint + TM - 1) / TM;

@@ -6,17 +6,12 @@
 
 namespace gfpp {
 
+// SM count of the CURRENT device (one process may drive several GPUs: nothing here is cached process-wide).
 inline int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;
-    }
-    return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+        return n;
+    return 148;
 }
 
 // blocks for a grid-stride kernel over n items: enough to cover n, capped at 8 resident waves,

@@ -258,7 +258,10 @@ __global__ void __launch_bounds__(256, 2) k_epilogue(const __grid_constant__ Tor
                 // bg = torso_color * alpha + bg * (1 - alpha); image = image + (1 - ws) * bg; clamp(0, 1)
                 const float bg = a.has_torso ? __fadd_rn(__fmul_rn(tc[c], ta), __fmul_rn(bgc, __fsub_rn(1.0f, ta))) : bgc;
                 const float v = __fadd_rn(a.image[3 * g + c], __fmul_rn(__fsub_rn(1.0f, ws), bg));
-                a.rgb_map[3 * g + c] = fminf(fmaxf(v, 0.f), 1.f);
+                const float vc = fminf(fmaxf(v, 0.f), 1.f);
+                if (a.rgb_map) a.rgb_map[3 * g + c] = vc;
+                // (rgb * 255).int() -> uint8: what the driver hands the video writer (genefacepp_infer.py:469, 505)
+                if (a.rgb_u8) a.rgb_u8[3 * g + c] = (unsigned char)(int)__fmul_rn(vc, 255.0f);
                 if (a.torso_rgb) a.torso_rgb[3 * g + c] = bg;
             }
             if (a.torso_alpha) a.torso_alpha[g] = ta;
@@ -306,12 +309,9 @@ cudaError_t launch_torso_frame_bias(const TorsoArgs &a, const float *w_def0, con
 }
 
 cudaError_t launch_epilogue(const TorsoArgs &a, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // function attributes are per device: set on every launch (a few microseconds), never cached process-wide
+    cudaError_t e = cudaFuncSetAttribute(k_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
     const int tiles = a.n_frames * ((a.n_rays + TP - 1) / TP);
     int blocks = 2 * sm_count();
     if (tiles < blocks) blocks = tiles > 0 ? tiles : 1;

@@ -26,7 +26,8 @@ struct TorsoArgs {
     int n_frames, n_rays;
     const float *image;     // [F,N,3] premultiplied head colour
     const float *wsum;      // [F,N]
-    float *rgb_map;         // [F,N,3]
+    float *rgb_map;         // [F,N,3] or nullptr
+    unsigned char *rgb_u8;  // [F,N,3] (uint8)(int)(rgb*255) or nullptr
     float *torso_alpha;     // [F,N] or nullptr
     float *torso_rgb;       // [F,N,3] or nullptr
     float *deform;          // [F,N,2] or nullptr

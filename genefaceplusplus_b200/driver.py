@@ -32,7 +32,7 @@ def cond_feat_from_windows(model, cond_wins, eye_area_percent=None):
                 eye = torch.as_tensor(eye_area_percent, dtype=torch.float32).reshape(T)
             feat = model._add_blink(feat, eye, T)
         feat = feat.view(T, S, -1)
-        feat = model.cond_att_net.forward_batched(feat) if model.with_att else feat[:, 0]
+        feat = model.cond_att_net.forward_batched(feat) if model.with_att else feat[:, S // 2]   # centre row, like cal_cond_feat_clip
     return feat
 
 

@@ -296,7 +296,10 @@ class RADNeRF(nn.Module):
         dev = self.density_bitfield.device
         if dev.type != "cuda":
             raise _capi.GfppError("model is not on a CUDA device: libgfpp has no CPU path (call .cuda())")
-        key = (float(self.density_scale), getattr(self, "mean_density_torso", None), dev.index, self.mlp_precision)
+        # in-place edits of the occupancy / tables / weights bump tensor._version: the packed copies are then rebuilt
+        vers = tuple(int(t._version) for t in (self.density_bitfield, self.position_embedder.embeddings, self.ambient_embedder.embeddings,
+                                               self.ambient_net.net[0].weight, self.sigma_net.net[0].weight, self.color_net.net[0].weight))
+        key = (float(self.density_scale), getattr(self, "mean_density_torso", None), dev.index, self.mlp_precision, vers)
         if self._packed is not None and self._packed[0] == key:
             return self._packed
         L = _capi.lib()
@@ -316,10 +319,14 @@ class RADNeRF(nn.Module):
     # ------------------------------------------------------------------ core call
     def render_frames(self, cond_feat, *, rays_o=None, rays_d=None, poses_c2w=None, intrinsics=None, H=None, W=None,
                       pose6=None, bg_coords=None, bg_color=None, dt_gamma=0.0, max_steps=1024, T_thresh=1e-4,
-                      want_torso_maps=True, want_stats=False):
+                      want_torso_maps=True, want_stats=False, rgb_out=None, u8_out=None, want_aux=True):
         """Render F frames with one call into libgfpp.  Returns a dict of device tensors with a leading F axis.
 
-        Either (rays_o, rays_d) [F,N,3] or (poses_c2w [F,4,4], intrinsics, H, W) must be given."""
+        Either (rays_o, rays_d) [F,N,3] or (poses_c2w [F,4,4], intrinsics, H, W) must be given.
+        rgb_out: optional contiguous fp32 [F,N,3] device view the kernel writes `rgb_map` into (e.g. a slice of the clip buffer:
+        no copy afterwards); u8_out: optional contiguous uint8 [F,N,3] view that receives the video frame `(rgb*255).int()`
+        straight from the epilogue kernel -- with u8_out and no rgb_out no fp32 frame is written at all.
+        want_aux=False skips the depth / weights_sum result tensors (they stay in the workspace)."""
         if self.training:
             raise NotImplementedError("libgfpp implements the inference branch only (renderer.py:340-384)")
         _, packed, model, _keep = self._ensure_packed()
@@ -331,12 +338,16 @@ class RADNeRF(nn.Module):
         fr = _capi.Frames()
         hold = [cond_feat]
         if rays_o is not None:
+            if rays_d is None or rays_d.numel() != rays_o.numel() or rays_o.numel() % (3 * Fn):
+                raise ValueError(f"rays_o / rays_d must both be [{Fn},N,3]")
             rays_o = rays_o.to(dev, f32).reshape(Fn, -1, 3).contiguous()
             rays_d = rays_d.to(dev, f32).reshape(Fn, -1, 3).contiguous()
             N = rays_o.shape[1]
             fr.rays_o, fr.rays_d = rays_o.data_ptr(), rays_d.data_ptr()
             hold += [rays_o, rays_d]
         else:
+            if poses_c2w is None or poses_c2w.numel() != Fn * 16:
+                raise ValueError(f"poses_c2w must be [{Fn},4,4] (one pose per conditioning row)")
             poses_c2w = poses_c2w.to(dev, f32).reshape(Fn, 16).contiguous()
             N = H * W
             fr.poses_c2w = poses_c2w.data_ptr()
@@ -346,6 +357,10 @@ class RADNeRF(nn.Module):
         fr.n_frames, fr.n_rays = Fn, N
         fr.cond_feat = cond_feat.data_ptr()
         if self.has_torso:
+            if pose6 is None or pose6.numel() != Fn * 6:
+                raise ValueError(f"pose6 must be [{Fn},6]")
+            if bg_coords is None or bg_coords.numel() != N * 2:
+                raise ValueError(f"bg_coords must be [{N},2] (one row per ray)")
             pose6 = pose6.to(dev, f32).reshape(Fn, 6).contiguous()
             bg_coords = bg_coords.to(dev, f32).reshape(N, 2).contiguous()
             fr.torso_pose6, fr.bg_coords = pose6.data_ptr(), bg_coords.data_ptr()
@@ -356,15 +371,32 @@ class RADNeRF(nn.Module):
             bg_color = bg_color.to(dev, f32).reshape(-1, 3)
             if bg_color.shape[0] == 1:
                 bg_color = bg_color.expand(N, 3)
+            elif bg_color.shape[0] != N:
+                raise ValueError(f"bg_color must have 1 or {N} rows (one per ray, shared by all frames), got {bg_color.shape[0]}")
             bg_color = bg_color.contiguous()
             fr.bg_color = bg_color.data_ptr()
             hold.append(bg_color)
         fr.dt_gamma, fr.max_steps, fr.T_thresh = float(dt_gamma), int(max_steps), float(T_thresh)
 
         out = _capi.Outputs()
-        res = {"rgb_map": torch.empty(Fn, N, 3, device=dev, dtype=f32), "depth_map": torch.empty(Fn, N, device=dev, dtype=f32),
-               "weights_sum": torch.empty(Fn, N, device=dev, dtype=f32)}
-        out.rgb_map, out.depth_map, out.weights_sum = res["rgb_map"].data_ptr(), res["depth_map"].data_ptr(), res["weights_sum"].data_ptr()
+        res = {}
+        if rgb_out is not None:
+            if rgb_out.dtype != f32 or not rgb_out.is_contiguous() or rgb_out.numel() != Fn * N * 3 or rgb_out.device != dev:
+                raise ValueError(f"rgb_out must be a contiguous fp32 [{Fn},{N},3] tensor on {dev}")
+            res["rgb_map"] = rgb_out.view(Fn, N, 3)
+        elif u8_out is None:
+            res["rgb_map"] = torch.empty(Fn, N, 3, device=dev, dtype=f32)
+        if u8_out is not None:
+            if u8_out.dtype != torch.uint8 or not u8_out.is_contiguous() or u8_out.numel() != Fn * N * 3 or u8_out.device != dev:
+                raise ValueError(f"u8_out must be a contiguous uint8 [{Fn},{N},3] tensor on {dev}")
+            res["rgb_u8"] = u8_out.view(Fn, N, 3)
+            out.rgb_u8 = u8_out.data_ptr()
+        if "rgb_map" in res:
+            out.rgb_map = res["rgb_map"].data_ptr()
+        if want_aux:
+            res["depth_map"] = torch.empty(Fn, N, device=dev, dtype=f32)
+            res["weights_sum"] = torch.empty(Fn, N, device=dev, dtype=f32)
+            out.depth_map, out.weights_sum = res["depth_map"].data_ptr(), res["weights_sum"].data_ptr()
         if self.has_torso and want_torso_maps:
             res["torso_alpha_map"] = torch.empty(Fn, N, device=dev, dtype=f32)
             res["torso_rgb_map"] = torch.empty(Fn, N, 3, device=dev, dtype=f32)
@@ -415,9 +447,11 @@ class RADNeRF(nn.Module):
     @torch.no_grad()
     def render_clip(self, poses_c2w, intrinsics, H, W, cond_seq=None, cond_feat=None, bg_color=None, bg_coords=None, pose6=None,
                     dt_gamma=None, max_steps=None, T_thresh=1e-2, frames_per_call=64, out=None, want_stats=False,
-                    eye_area_percent=None):
+                    eye_area_percent=None, as_uint8=False):
         """Render a clip: poses_c2w [T,4,4], cond_seq [T,1,C] (or precomputed cond_feat [T,64]); eye_area_percent [T] for
-        add_eye_blink_cond models.  Returns rgb [T,H*W,3] on the model's device (fp32, clamped to [0,1])."""
+        add_eye_blink_cond models.  Returns rgb [T,H*W,3] on the model's device: fp32 clamped to [0,1], or -- as_uint8 -- the
+        uint8 video frames `(rgb*255).int()` (genefacepp_infer.py:469,505) written by the epilogue kernel itself.  `out`: optional
+        preallocated result buffer of that dtype; every call writes its frames straight into it."""
         dev = self.density_bitfield.device
         T = poses_c2w.shape[0]
         hp = self.hparams
@@ -430,15 +464,18 @@ class RADNeRF(nn.Module):
             from .scene import convert_poses
             pose6 = convert_poses(poses_c2w.cpu()).to(dev)
         N = H * W
-        rgb = out if out is not None else torch.empty(T, N, 3, device=dev, dtype=torch.float32)
+        odt = torch.uint8 if as_uint8 else torch.float32
+        rgb = out if out is not None else torch.empty(T, N, 3, device=dev, dtype=odt)
+        if rgb.dtype != odt or rgb.numel() != T * N * 3 or not rgb.is_contiguous():
+            raise ValueError(f"out must be a contiguous {odt} [{T},{N},3] tensor")
+        rgb = rgb.view(T, N, 3)
         stats = []
         for s in range(0, T, frames_per_call):
             e = min(T, s + frames_per_call)
             res = self.render_frames(cond_feat[s:e], poses_c2w=poses_c2w[s:e], intrinsics=intrinsics, H=H, W=W,
                                      pose6=pose6[s:e] if self.has_torso else None, bg_coords=bg_coords, bg_color=bg_color,
                                      dt_gamma=dt_gamma, max_steps=max_steps, T_thresh=T_thresh, want_torso_maps=False,
-                                     want_stats=want_stats)
-            rgb[s:e].copy_(res["rgb_map"])
+                                     want_stats=want_stats, want_aux=False, **({"u8_out": rgb[s:e]} if as_uint8 else {"rgb_out": rgb[s:e]}))
             if want_stats:
                 stats.append(res["stats"])
         if want_stats:

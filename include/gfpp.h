@@ -177,6 +177,9 @@ typedef struct {
     float *torso_rgb_map;         /* [F,N,3] or NULL (bg mixed with torso, radnerf_torso.py:187-189) */
     float *torso_deform;          /* [F,N,2] deformation for masked pixels, 0 elsewhere; or NULL */
     int32_t *stats;               /* [F,4] = {B_total, n_survivors, S_valid_samples, P_torso_pixels} or NULL */
+    uint8_t *rgb_u8;              /* [F,N,3] the frame as the video writer wants it, (uint8)(int)(rgb * 255) of the clamped colour
+                                   * (inference/genefacepp_infer.py:469,505), written by the epilogue kernel itself; or NULL.
+                                   * rgb_map may be NULL when rgb_u8 is given (then no fp32 frame is written at all) */
 } gfpp_outputs;
 
 GFPP_API size_t gfpp_render_workspace_bytes(uint32_t n_frames, uint32_t n_rays, uint32_t max_steps);
