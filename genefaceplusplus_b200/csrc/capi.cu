@@ -26,6 +26,7 @@ cudaError_t launch_occupancy_bounds(const uint8_t *, uint32_t, uint32_t, int *, 
 cudaError_t launch_coarse_occupancy(const uint8_t *, uint32_t, uint32_t, uint32_t *, cudaStream_t);
 cudaError_t launch_pack_quads(const GridMeta &, const float *, float *, uint32_t, cudaStream_t);
 cudaError_t launch_pack_octs(const GridMeta &, const float *, void *, uint32_t, cudaStream_t);
+cudaError_t launch_pack_octs_i16(const GridMeta &, const float *, void *, uint32_t, uint32_t *, float *, cudaStream_t);
 // tc_pack.cu
 cudaError_t launch_pack_tc_tile(const float *, int, int, int, int, int, int, int, int, unsigned char *, unsigned char *, cudaStream_t);
 cudaError_t launch_tc_selftest(const float *, int, const unsigned char *, const unsigned char *, int, int, int, int, float *, cudaStream_t);
@@ -124,12 +125,17 @@ struct ModelHost {
     int use_occ_box;
     int mlp_precision;
     HeadTcArgs tc;
+    // v2 head kernel (head_v2_kernel.cu): shared weight stream + resident tiles; valid when v2_ok
+    int v2_ok;
+    const unsigned char *v2_stream, *v2_res;
+    const float *v2_pos_step;       // robust mode: per-level step of the 16-bit position table
+    const float *amb0_src;          // ambient_net.net.0.weight [128,96] (its conditioning columns are folded per frame)
 };
 static_assert(sizeof(ModelHost) <= sizeof(gfpp_model), "gfpp_model opaque storage too small");
 constexpr uint32_t kMagic = 0x67667070u;  // "gfpp"
 
 struct PackedLayout {
-    size_t wide, narrow, wd0, wd1, wd2, wc0, wc1, wc2, occ, coarse, tc_hi, tc_lo, pos_quads, amb_quads, total;
+    size_t wide, narrow, wd0, wd1, wd2, wc0, wc1, wc2, occ, coarse, tc_hi, tc_lo, v2_stream, v2_res, v2_step, pos_quads, amb_quads, total;
 };
 
 // tensor-core weight stream: kHeadTcChunks (head_kernel.cuh)
@@ -162,6 +168,9 @@ PackedLayout packed_layout(uint32_t cascade = 8, uint32_t grid_size = 128, size_
     for (int c = 0; c < HEAD_TC_NCHUNK; ++c) tcb += (size_t)tc_chunk_bytes(c);
     L.tc_hi = take(tcb / 4);
     L.tc_lo = take(tcb / 4);
+    L.v2_stream = take((size_t)V2_NTILE_ROBUST * V2_TILE_BYTES / 4);
+    L.v2_res = take(V2_RES_BYTES / 4);
+    L.v2_step = take(64);          // 16 steps + 16 words of scratch for the per-level maxima
     L.pos_quads = take(pos_entries * 8);   // 32 bytes per entry
     L.amb_quads = take(amb_entries * 8);
     L.total = o;
@@ -170,7 +179,7 @@ PackedLayout packed_layout(uint32_t cascade = 8, uint32_t grid_size = 128, size_
 
 struct WorkLayout {
     size_t image, rays_t, wsum, depth, survivors, hits, zero_begin, hist, counters, B_total, valid, pcount, zero_end, bias_def,
-        bias_can, total;
+        bias_can, bias_amb, total;
 };
 
 WorkLayout work_layout(uint32_t F, uint32_t N, uint32_t max_steps) {
@@ -193,6 +202,7 @@ WorkLayout work_layout(uint32_t F, uint32_t N, uint32_t max_steps) {
     W.zero_end = o;
     W.bias_def = take((size_t)F * 64 * 4);
     W.bias_can = take((size_t)F * 32 * 4);
+    W.bias_amb = take((size_t)F * 128 * 4);
     W.total = o;
     return W;
 }
@@ -442,12 +452,38 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
     // packing below because that one clears everything from tc_hi to the END of the packed buffer
     const bool want_quads = getenv("GFPP_NO_QUADS") == nullptr;
     m.mlp_precision = (int)d->mlp_precision;
-    if (d->mlp_precision > 3) return fail(GFPP_ERR_UNSUPPORTED, "model_pack: mlp_precision must be 0..3%s");
-    if (d->mlp_precision != 0) {
+    if (d->mlp_precision > 4) return fail(GFPP_ERR_UNSUPPORTED, "model_pack: mlp_precision must be 0..4%s");
+    const bool robust = d->mlp_precision == 4;
+    if (d->mlp_precision != 0) CKN(cudaMemsetAsync(base + L.tc_hi, 0, L.pos_quads - L.tc_hi, st));
+    m.amb0_src = d->ambient_w[0];
+    if (d->mlp_precision == 1 || robust) {
+        // v2 weight images: streamed tiles in the kernel's schedule order (head_kernel.cuh), then the resident block
+        unsigned char *vs = (unsigned char *)(base + L.v2_stream), *vr = (unsigned char *)(base + L.v2_res);
+        struct T { const float *w; int ld, row0, col0, kc; bool split; };
+        const T tiles[10] = {{d->ambient_w[0], 96, 0, 0, 32, true},  {d->ambient_w[1], 128, 0, 0, 64, true}, {d->ambient_w[1], 128, 0, 64, 64, true},
+                             {d->sigma_w[0], 64, 0, 0, 64, false},   {d->sigma_w[1], 128, 0, 0, 64, false},  {d->sigma_w[1], 128, 0, 64, 64, false},
+                             {d->sigma_w[2], 128, 1, 0, 64, false},  {d->sigma_w[2], 128, 1, 64, 64, false},
+                             {d->color_w[0], col0_in, 0, 16, 64, false}, {d->color_w[0], col0_in, 0, 80, 64, false}};
+        int ti = 0;
+        for (int c = 0; c < 10; ++c) {
+            const bool sp = robust && tiles[c].split;
+            unsigned char *hi = vs + (size_t)ti * V2_TILE_BYTES, *lo = sp ? hi + V2_TILE_BYTES : nullptr;
+            CK(launch_pack_tc_tile(tiles[c].w, tiles[c].ld, tiles[c].row0, tiles[c].col0, 128, tiles[c].kc, 0, 0, 0, hi, lo, st));
+            ti += sp ? 2 : 1;
+        }
+        for (int kt = 0; kt < 2; ++kt) {
+            CK(launch_pack_tc_tile(d->ambient_w[2], 128, 0, kt * 64, amb_dim, 64, 0, 0, 0, vr + V2_RES_AMBN_HI + kt * 2048,
+                                   robust ? vr + V2_RES_AMBN_LO + kt * 2048 : nullptr, st));
+            CK(launch_pack_tc_tile(d->sigma_w[2], 128, 0, kt * 64, 1, 64, 0, 0, 0, vr + V2_RES_SIGROW + kt * 2048, nullptr, st));
+            CK(launch_pack_tc_tile(d->color_w[1], 128, 0, kt * 64, 3, 64, 0, 0, 0, vr + V2_RES_COLN + kt * 2048, nullptr, st));
+        }
+        CK(launch_pack_tc_tile(d->color_w[0], col0_in, 0, 0, 128, 16, 0, 1, 0, vr + V2_RES_COLSH, nullptr, st));
+        m.v2_stream = vs; m.v2_res = vr;
+    }
+    if (d->mlp_precision != 0 && !robust) {
         const int bf16 = d->mlp_precision != 1;
         const bool split = d->mlp_precision == 2;
         unsigned char *thi = (unsigned char *)(base + L.tc_hi), *tlo = (unsigned char *)(base + L.tc_lo);
-        CKN(cudaMemsetAsync(base + L.tc_hi, 0, L.pos_quads - L.tc_hi, st));
         const float *lw[6] = {d->ambient_w[0], d->ambient_w[1], d->sigma_w[0], d->sigma_w[1], d->sigma_w[2], d->color_w[0]};
         const int lld[6] = {96, 128, 64, 128, 128, col0_in};
         int boff = 0;
@@ -466,9 +502,14 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
 
     // fp16 mode: fp16 "octs" (one 32-byte sector per sample-level; tables rounded to fp16 like the reference under
     // autocast); every other mode: fp32 "quads" (bit-identical values).  Both occupy the same 32 bytes per entry.
-    const bool want_octs = want_quads && d->mlp_precision == 1 && getenv("GFPP_NO_OCTS") == nullptr;
+    const bool want_octs = want_quads && (d->mlp_precision == 1 || robust) && getenv("GFPP_NO_OCTS") == nullptr;
     if (want_quads && m.pos_gm.quad_ok && m.pos_gm.dim == 3) {
-        if (want_octs) {
+        if (want_octs && robust) {   // 16-bit fixed point, one step per level: the position table's rounding is what the ambient net amplifies
+            float *step = (float *)(base + L.v2_step);
+            CK(launch_pack_octs_i16(m.pos_gm, d->position_grid.embeddings, base + L.pos_quads, (uint32_t)pos_entries, (uint32_t *)(step + 16), step, st));
+            m.pos_octs = (const uint4 *)(base + L.pos_quads);
+            m.v2_pos_step = step;
+        } else if (want_octs) {
             CK(launch_pack_octs(m.pos_gm, d->position_grid.embeddings, base + L.pos_quads, (uint32_t)pos_entries, st));
             m.pos_octs = (const uint4 *)(base + L.pos_quads);
         } else {
@@ -486,6 +527,9 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
         }
     }
 
+    m.v2_ok = (m.v2_stream && m.pos_octs && m.amb_octs && m.pos_gm.num_levels == 16 && m.amb_gm.num_levels == 16 && amb_dim == 3) ? 1 : 0;
+    if (robust && !m.v2_ok)
+        return fail(GFPP_ERR_UNSUPPORTED, "model_pack: the robust mode needs 3-D tiled position and ambient grids (sector-packed tables)%s");
     m.has_torso = d->has_torso;
     if (d->has_torso) {
         for (int i = 0; i < 3; ++i)
@@ -600,14 +644,23 @@ int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfp
     a.pass = 1;
     a.cursor = counters + 0;
     CK(launch_ray_setup(a, st));
+    // fp16 / robust: the row-owner kernel (head_v2_kernel.cu); GFPP_HEAD_V1 keeps the first-generation fp16 kernel for A/B runs
+    const bool use_v2 = m.v2_ok && (m.mlp_precision == 4 || (m.mlp_precision == 1 && getenv("GFPP_HEAD_V1") == nullptr));
+    if (m.mlp_precision == 4 && !use_v2) return fail(GFPP_ERR_UNSUPPORTED, "render_frames: robust mode unavailable for this model%s");
+    HeadV2Args v2;
+    v2.w_stream = m.v2_stream; v2.w_res = m.v2_res; v2.pos_step = m.v2_pos_step;
+    v2.amb_bias = (const float *)(ws + W.bias_amb);
+    if (use_v2) CK(launch_amb_frame_bias(m.amb0_src, fr->cond_feat, a.n_frames, (float *)(ws + W.bias_amb), st));
     if (g_profile) CKN(cudaEventRecord(g_ev[0], st));
     if (m.mlp_precision == 0) CK(launch_head(a, -1, st));
+    else if (use_v2) CK(launch_head_v2(a, v2, m.mlp_precision, st));
     else CK(launch_head_tc(a, m.tc, m.mlp_precision, -1, st));
     if (g_profile) CKN(cudaEventRecord(g_ev[1], st));
     CK(launch_schedule(a.hist, a.n_frames, a.n_rays, a.max_steps, a.B_total, st));
     a.pass = 2;
     a.cursor = counters + 1;
     if (m.mlp_precision == 0) CK(launch_head(a, -1, st));
+    else if (use_v2) CK(launch_head_v2(a, v2, m.mlp_precision, st));
     else CK(launch_head_tc(a, m.tc, m.mlp_precision, -1, st));
     if (g_profile) CKN(cudaEventRecord(g_ev[2], st));
     CK(launch_epilogue(t, st));

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "gather8.cuh"
 #include "head_common.cuh"
 #include "head_kernel.cuh"
 #include "launch.cuh"
@@ -193,64 +194,6 @@ __device__ __noinline__ void epilogue_wide(unsigned char *a_hi, unsigned char *a
     }
 }
 
-// fp16-oct fast path: EIGHT consecutive levels of a 3-D grid for one sample -> 16 features (two operand chunks).
-// `lvl` points at the levels' metadata in SHARED memory (two 16-byte words per level, stage_level_meta): reading GridMeta
-// through a reference to the kernel parameters costs six dependent generic loads per level on the address path.
-// All eight 32-byte loads (one sm_100 256-bit LDG per oct: half the L1 wavefronts of two 128-bit loads) are issued before
-// the first is consumed, so the thread pays one L2 round trip per table.
-// Out of line on purpose (I-cache, register budget of the 2-CTA kernel).
-__device__ __noinline__ void lookup8o(const uint4 *lvl, float align_off, bool smoothstep, const uint4 *__restrict__ octs, float u, float v,
-                                      float w, float (&f)[16]) {
-    float fx[8], fy[8], fz[8];
-    uint4 lo4[8], hi4[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint4 m0 = lvl[2 * j], m1 = lvl[2 * j + 1];   // {scale, mul1, mul2, offset}, {hmask, hsize, -, -}
-        const float s = __uint_as_float(m0.x);
-        float px = __fadd_rn(__fmul_rn(u, s), align_off), py = __fadd_rn(__fmul_rn(v, s), align_off),
-              pz = __fadd_rn(__fmul_rn(w, s), align_off);
-        const float x0 = floorf(px), y0 = floorf(py), z0 = floorf(pz);
-        px -= x0; py -= y0; pz -= z0;
-        if (smoothstep) {
-            px = px * px * (3.0f - 2.0f * px);
-            py = py * py * (3.0f - 2.0f * py);
-            pz = pz * pz * (3.0f - 2.0f * pz);
-        }
-        fx[j] = px; fy[j] = py; fz[j] = pz;
-        uint32_t q = (uint32_t)x0 + (uint32_t)y0 * m0.y + (uint32_t)z0 * m0.z;
-        if (m1.x) q &= m1.x;                 // grid_mod (common.cuh)
-        else if (q >= m1.y) q %= m1.y;
-        ldg256_na(octs + 2 * ((size_t)m0.w + q), lo4[j], hi4[j]);   // the whole 32-byte oct in one request
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t c[8] = {lo4[j].x, lo4[j].y, lo4[j].z, lo4[j].w, hi4[j].x, hi4[j].y, hi4[j].z, hi4[j].w};
-        const float wx[2] = {1.0f - fx[j], fx[j]}, wy[2] = {1.0f - fy[j], fy[j]}, wz[2] = {1.0f - fz[j], fz[j]};
-        float ax = 0.f, ay = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float2 e = __half22float2(*reinterpret_cast<const __half2 *>(&c[i]));
-            const float wgt = wx[i & 1] * wy[(i >> 1) & 1] * wz[(i >> 2) & 1];
-            ax += wgt * e.x;
-            ay += wgt * e.y;
-        }
-        f[2 * j] = ax;
-        f[2 * j + 1] = ay;
-    }
-    if (u < 0.f || u > 1.f || v < 0.f || v > 1.f || w < 0.f || w > 1.f) {   // outside the grid: zeros (gridencoder.cu:108-118)
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = 0.f;
-    }
-}
-// per-level metadata of one grid -> shared memory, the layout lookup8o reads
-__device__ __forceinline__ void stage_level_meta(const GridMeta &gm, uint4 *lvl, int tid) {
-    if (tid < GFPP_MAX_LEVELS) {
-        const bool on = (uint32_t)tid < gm.num_levels;
-        lvl[2 * tid] = on ? make_uint4(__float_as_uint(gm.scale[tid]), gm.mul1[tid], gm.mul2[tid], gm.offset[tid]) : make_uint4(0, 0, 0, 0);
-        lvl[2 * tid + 1] = on ? make_uint4(gm.hmask[tid], gm.hsize[tid], 0u, 0u) : make_uint4(0, 1u, 0, 0);
-    }
-}
-
 // Four consecutive levels of a grid -> 8 features (one 16-byte operand chunk): the fp32 quad layout (bf16x3 / bf16 modes) or
 // the reference layout.  Out of line on purpose (I-cache).
 __device__ __noinline__ void lookup4(const GridMeta &gm, const float2 *__restrict__ table, const float4 *__restrict__ quads, int l0,
@@ -290,8 +233,8 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
         s.nw[3 * 128 + i] = a.narrow[4 * 128 + i];
     }
     if (tid < 128) s.bias[tid] = a.narrow[7 * 128 + tid];
-    stage_level_meta(a.pos_gm, s.lvl[0], tid);
-    stage_level_meta(a.amb_gm, s.lvl[1], tid);
+    stage_level_meta(a.pos_gm, nullptr, s.lvl[0], tid);
+    stage_level_meta(a.amb_gm, nullptr, s.lvl[1], tid);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -337,7 +280,10 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
             }
             if (a.pos_octs) {   // thread (slot, lg) owns levels lg*8 .. lg*8+7 = operand chunks 2lg, 2lg+1
                 float f[16];
-                if (v) lookup8o(&s.lvl[0][lg * 16], a.pos_gm.align_off, a.pos_gm.interp == 1, a.pos_octs, u, vv, w, f);
+                if (v) {
+                    if (a.pos_gm.interp == 1) lookup8<true, OCT_F16>(&s.lvl[0][lg * 16], a.pos_gm.align_off, a.pos_octs, u, vv, w, f);
+                    else lookup8<false, OCT_F16>(&s.lvl[0][lg * 16], a.pos_gm.align_off, a.pos_octs, u, vv, w, f);
+                }
                 else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = 0.f;
@@ -419,7 +365,10 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
             }
             if (a.amb_octs) {
                 float f[16];
-                if (v) lookup8o(&s.lvl[1][lg * 16], a.amb_gm.align_off, a.amb_gm.interp == 1, a.amb_octs, u, vv, w, f);
+                if (v) {
+                    if (a.amb_gm.interp == 1) lookup8<true, OCT_F16>(&s.lvl[1][lg * 16], a.amb_gm.align_off, a.amb_octs, u, vv, w, f);
+                    else lookup8<false, OCT_F16>(&s.lvl[1][lg * 16], a.amb_gm.align_off, a.amb_octs, u, vv, w, f);
+                }
                 else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = 0.f;

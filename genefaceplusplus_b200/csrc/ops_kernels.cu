@@ -219,7 +219,59 @@ __global__ void k_pack_octs(GridMeta gm, const float2 *__restrict__ table, uint4
     }
 }
 
+// 16-bit fixed-point octs (gather8.cuh OCT_I16): per-level step = max|T_l| / 32767, q = rn(T / step)
+__global__ void k_level_absmax(GridMeta gm, const float2 *__restrict__ table, uint32_t total, uint32_t *__restrict__ amax_bits) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int l = 0;
+#pragma unroll 1
+        for (int k = 1; k < (int)gm.num_levels; ++k)
+            if (i >= gm.offset[k]) l = k;
+        const float2 e = table[i];
+        const float m = fmaxf(fabsf(e.x), fabsf(e.y));
+        if (m > 0.f && !(m != m)) atomicMax(amax_bits + l, __float_as_uint(m));   // non-negative floats order like their bit patterns
+    }
+}
+__global__ void k_level_step(const uint32_t *__restrict__ amax_bits, int n_levels, float *__restrict__ step) {
+    const int l = threadIdx.x;
+    if (l < n_levels) {
+        const float m = __uint_as_float(amax_bits[l]);
+        step[l] = m > 0.f ? m / 32767.0f : 1.0f;
+    }
+}
+__global__ void k_pack_octs_i16(GridMeta gm, const float2 *__restrict__ table, uint4 *__restrict__ octs, uint32_t total,
+                                const float *__restrict__ step) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int l = 0;
+#pragma unroll 1
+        for (int k = 1; k < (int)gm.num_levels; ++k)
+            if (i >= gm.offset[k]) l = k;
+        const uint32_t q = i - gm.offset[l], m1 = gm.mul1[l], m2 = gm.mul2[l];
+        const float2 *tb = table + gm.offset[l];
+        const float inv = 1.0f / step[l];
+        uint32_t w[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float2 e = tb[grid_mod(gm, l, q + (c & 1) + ((c & 2) ? m1 : 0u) + ((c & 4) ? m2 : 0u))];
+            const int qx = max(-32767, min(32767, __float2int_rn(e.x * inv))), qy = max(-32767, min(32767, __float2int_rn(e.y * inv)));
+            w[c] = ((uint32_t)qx & 0xFFFFu) | ((uint32_t)qy << 16);
+        }
+        octs[2 * (size_t)i] = make_uint4(w[0], w[1], w[2], w[3]);
+        octs[2 * (size_t)i + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
+// scratch: 16 uint32 (zeroed here); step: 16 floats
+cudaError_t launch_pack_octs_i16(const GridMeta &gm, const float *table, void *octs, uint32_t total, uint32_t *scratch, float *step,
+                                 cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 16 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    k_level_absmax<<<grid_for(total, 256), 256, 0, st>>>(gm, (const float2 *)table, total, scratch);
+    k_level_step<<<1, 32, 0, st>>>(scratch, (int)gm.num_levels, step);
+    k_pack_octs_i16<<<grid_for(total, 256), 256, 0, st>>>(gm, (const float2 *)table, (uint4 *)octs, total, step);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pack_octs(const GridMeta &gm, const float *table, void *octs, uint32_t total, cudaStream_t st) {
     k_pack_octs<<<grid_for(total, 256), 256, 0, st>>>(gm, (const float2 *)table, (uint4 *)octs, total);
     return cudaGetLastError();

@@ -27,7 +27,7 @@ from . import _capi
 from .config import GridLayout, cascade_count
 
 
-MLP_PRECISIONS = {"fp32": 0, "fp16": 1, "bf16x3": 2, "bf16": 3}
+MLP_PRECISIONS = {"fp32": 0, "fp16": 1, "bf16x3": 2, "bf16": 3, "robust": 4}
 
 
 # ------------------------------------------------------------------------------------------------ small modules
@@ -167,7 +167,8 @@ class RADNeRF(nn.Module):
         if not shape_ok:
             raise NotImplementedError("libgfpp kernels are built for the May architecture (hidden 128, 3/3/2 layers, cond 64)")
         # arithmetic of the head MLP GEMMs (gfpp_model_desc.mlp_precision): "fp32" (CUDA-core FFMA), "fp16" (tcgen05, what the
-        # reference runs under autocast), "bf16x3" (tcgen05 hi/lo split, ~fp32 accuracy), "bf16" (tcgen05)
+        # reference runs under autocast), "bf16x3" (tcgen05 hi/lo split, ~fp32 accuracy), "bf16" (tcgen05), "robust" (tcgen05 fp16
+        # with the hi/lo split on the ambient net only + a 16-bit fixed-point position table: holds 1e-3 on well-conditioned scenes)
         self.mlp_precision = hparams.get("gfpp_mlp_precision", "fp32")
         self._packed = None  # (key, packed_dev, Model, keepalive)
         self._workspace = None

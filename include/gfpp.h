@@ -130,7 +130,10 @@ typedef struct {
     uint32_t torso_code_dim;            /* 8 */
     /* arithmetic of the head MLP GEMMs: 0 = fp32 FFMA (CUDA cores), 1 = fp16 operands on tcgen05 tensor cores with
      * fp32 accumulation (what the reference runs under autocast), 2 = bf16 hi/lo split x3 on tcgen05 (~fp32 accuracy),
-     * 3 = bf16 x1.  Everything else (marching, gather, compositing, torso) is fp32 in every mode. */
+     * 3 = bf16 x1, 4 = "robust": fp16 on tcgen05 with the hi/lo split (3 MMAs per k-step, ~22 mantissa bits) on the ambient
+     * net only and a 16-bit fixed-point position table -- the two roundings the field amplifies; holds 1e-3 max-abs on
+     * well-conditioned (trained-like) scenes where plain fp16 does not.  Modes 1 and 4 run the row-owner kernel
+     * (head_v2_kernel.cu).  Everything else (marching, compositing, torso) is fp32 in every mode. */
     uint32_t mlp_precision;
 } gfpp_model_desc;
 
