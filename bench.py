@@ -433,7 +433,8 @@ def _main(args, out):
         line = {"metric": metric_name(args), "value": fps,
                 "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"fp32": "f32", "fp16": "f16 operands, f32 accumulate (tcgen05)", "bf16x3": "bf16 hi/lo split x3, f32 accumulate (tcgen05)", "bf16": "bf16 operands, f32 accumulate (tcgen05)"}[args.precision],
+                "dtype": {"fp32": "f32", "fp16": "f16 operands, f32 accumulate (tcgen05)", "bf16x3": "bf16 hi/lo split x3, f32 accumulate (tcgen05)", "bf16": "bf16 operands, f32 accumulate (tcgen05)",
+                          "robust": "f16 operands, f32 accumulate (tcgen05); hi/lo split x3 on the ambient net, 16-bit fixed-point position table"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "mlp_precision": args.precision, "frames_per_gpu_per_step": T, "frames_per_call": args.frames_per_call,
                            "S_valid_samples_per_frame": S_per_frame, "P_torso_pixels_per_frame": P_per_frame, "B_total": int(st[0, 0]),

@@ -202,7 +202,7 @@ WorkLayout work_layout(uint32_t F, uint32_t N, uint32_t max_steps) {
     W.zero_end = o;
     W.bias_def = take((size_t)F * 64 * 4);
     W.bias_can = take((size_t)F * 32 * 4);
-    W.bias_amb = take((size_t)F * 128 * 4);
+    W.bias_amb = take((size_t)F * 64 * 2 * 2);   // fp16 hi + lo images of the conditioning vectors (v2 head kernel)
     W.total = o;
     return W;
 }
@@ -460,12 +460,13 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
         // v2 weight images: streamed tiles in the kernel's schedule order (head_kernel.cuh), then the resident block
         unsigned char *vs = (unsigned char *)(base + L.v2_stream), *vr = (unsigned char *)(base + L.v2_res);
         struct T { const float *w; int ld, row0, col0, kc; bool split; };
-        const T tiles[10] = {{d->ambient_w[0], 96, 0, 0, 32, true},  {d->ambient_w[1], 128, 0, 0, 64, true}, {d->ambient_w[1], 128, 0, 64, 64, true},
+        const T tiles[11] = {{d->ambient_w[0], 96, 0, 0, 64, true},  {d->ambient_w[0], 96, 0, 64, 32, true},
+                             {d->ambient_w[1], 128, 0, 0, 64, true}, {d->ambient_w[1], 128, 0, 64, 64, true},
                              {d->sigma_w[0], 64, 0, 0, 64, false},   {d->sigma_w[1], 128, 0, 0, 64, false},  {d->sigma_w[1], 128, 0, 64, 64, false},
                              {d->sigma_w[2], 128, 1, 0, 64, false},  {d->sigma_w[2], 128, 1, 64, 64, false},
                              {d->color_w[0], col0_in, 0, 16, 64, false}, {d->color_w[0], col0_in, 0, 80, 64, false}};
         int ti = 0;
-        for (int c = 0; c < 10; ++c) {
+        for (int c = 0; c < 11; ++c) {
             const bool sp = robust && tiles[c].split;
             unsigned char *hi = vs + (size_t)ti * V2_TILE_BYTES, *lo = sp ? hi + V2_TILE_BYTES : nullptr;
             CK(launch_pack_tc_tile(tiles[c].w, tiles[c].ld, tiles[c].row0, tiles[c].col0, 128, tiles[c].kc, 0, 0, 0, hi, lo, st));
@@ -649,8 +650,9 @@ int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfp
     if (m.mlp_precision == 4 && !use_v2) return fail(GFPP_ERR_UNSUPPORTED, "render_frames: robust mode unavailable for this model%s");
     HeadV2Args v2;
     v2.w_stream = m.v2_stream; v2.w_res = m.v2_res; v2.pos_step = m.v2_pos_step;
-    v2.amb_bias = (const float *)(ws + W.bias_amb);
-    if (use_v2) CK(launch_amb_frame_bias(m.amb0_src, fr->cond_feat, a.n_frames, (float *)(ws + W.bias_amb), st));
+    v2.cond_hi = (const unsigned char *)(ws + W.bias_amb);
+    v2.cond_lo = v2.cond_hi + (size_t)fr->n_frames * 128;
+    if (use_v2) CK(launch_cond_images(fr->cond_feat, a.n_frames, ws + W.bias_amb, ws + W.bias_amb + (size_t)fr->n_frames * 128, st));
     if (g_profile) CKN(cudaEventRecord(g_ev[0], st));
     if (m.mlp_precision == 0) CK(launch_head(a, -1, st));
     else if (use_v2) CK(launch_head_v2(a, v2, m.mlp_precision, st));

@@ -35,9 +35,9 @@ __device__ __forceinline__ float2 unpack_i16x2(uint32_t w) {
     return make_float2(lo - 12615680.0f, hi - 12615680.0f);   // 12582912 + 32768
 }
 
-template <bool SMOOTH, int FMT>
-__device__ __noinline__ void lookup8(const uint4 *lvl, float align_off, const uint4 *__restrict__ octs, float u, float v, float w,
-                                     float (&f)[16]) {
+template <int FMT>
+__device__ __forceinline__ void lookup8(const uint4 *lvl, float align_off, bool smooth, const uint4 *__restrict__ octs, float u, float v, float w,
+                                        float (&f)[16]) {
     float fx[8], fy[8], fz[8];
     uint4 lo4[8], hi4[8];
 #pragma unroll
@@ -48,7 +48,7 @@ __device__ __noinline__ void lookup8(const uint4 *lvl, float align_off, const ui
               pz = __fadd_rn(__fmul_rn(w, s), align_off);
         const float x0 = floorf(px), y0 = floorf(py), z0 = floorf(pz);
         px -= x0; py -= y0; pz -= z0;
-        if (SMOOTH) {
+        if (smooth) {   // warp-uniform
             px = px * px * (3.0f - 2.0f * px);
             py = py * py * (3.0f - 2.0f * py);
             pz = pz * pz * (3.0f - 2.0f * pz);

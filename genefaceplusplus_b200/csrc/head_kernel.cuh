@@ -77,19 +77,20 @@ size_t head_tc_smem_bytes(bool split);
 
 // ---- v2 (head_v2_kernel.cu): one CTA per SM, 2-3 row-owner slots of 128 samples sharing one weight stream ----
 constexpr int V2_TILE_BYTES = 16384;            // one streamed weight tile: 128 rows x 64 k x 2 B (SW128)
-// Streamed tiles of one super-batch, in order.  fp16: amb0 | amb1 a,b | sig0 | sig1 a,b | sig2 a,b (geo rows) | col0 a,b (geo columns);
-// robust: every ambient tile is followed by its lo image.
-constexpr int V2_NTILE_X1 = 10, V2_NTILE_ROBUST = 13;
+// Streamed tiles of one super-batch, in order.  fp16: amb0 a (k 0-63: position features + conditioning 0-31), b (k 64-95: conditioning
+// 32-63) | amb1 a,b | sig0 | sig1 a,b | sig2 a,b (geo rows) | col0 a,b (geo columns); robust: every ambient tile is followed by its lo image.
+constexpr int V2_NTILE_X1 = 11, V2_NTILE_ROBUST = 15;
 // Resident small tiles (loaded once per CTA): 16-row N tiles of the narrow layers, 2 KB per 64-wide K tile, and the K16 SH tile
 constexpr int V2_RES_AMBN_HI = 0, V2_RES_AMBN_LO = 4096, V2_RES_SIGROW = 8192, V2_RES_COLSH = 12288, V2_RES_COLN = 16384, V2_RES_BYTES = 20480;
 struct HeadV2Args {
     const unsigned char *w_stream;   // V2_NTILE_* tiles of V2_TILE_BYTES back to back
     const unsigned char *w_res;      // V2_RES_BYTES
-    const float *amb_bias;           // [F,128] fp32: conditioning columns of ambient L0 folded per frame (k_amb_frame_bias)
+    const unsigned char *cond_hi;    // [F,64] fp16: the frame's conditioning vector, pre-rounded (k_cond_images)
+    const unsigned char *cond_lo;    // [F,64] fp16 residuals (robust mode)
     const float *pos_step;           // [16] per-level step of the 16-bit fixed-point position table (robust mode) or nullptr
 };
 cudaError_t launch_head_v2(const HeadArgs &a, const HeadV2Args &t, int precision, cudaStream_t st);
-cudaError_t launch_amb_frame_bias(const float *w_amb0, const float *cond_feat, int n_frames, float *bias, cudaStream_t st);
+cudaError_t launch_cond_images(const float *cond_feat, int n_frames, void *cond_hi, void *cond_lo, cudaStream_t st);
 size_t head_v2_smem_bytes(bool robust);
 
 size_t head_smem_bytes();

@@ -194,6 +194,12 @@ __device__ __noinline__ void epilogue_wide(unsigned char *a_hi, unsigned char *a
     }
 }
 
+// out of line on purpose (I-cache, register budget of the 2-CTA kernel)
+__device__ __noinline__ void lookup8o(const uint4 *lvl, float align_off, bool smoothstep, const uint4 *__restrict__ octs, float u, float v,
+                                      float w, float (&f)[16]) {
+    lookup8<OCT_F16>(lvl, align_off, smoothstep, octs, u, v, w, f);
+}
+
 // Four consecutive levels of a grid -> 8 features (one 16-byte operand chunk): the fp32 quad layout (bf16x3 / bf16 modes) or
 // the reference layout.  Out of line on purpose (I-cache).
 __device__ __noinline__ void lookup4(const GridMeta &gm, const float2 *__restrict__ table, const float4 *__restrict__ quads, int l0,
@@ -280,10 +286,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
             }
             if (a.pos_octs) {   // thread (slot, lg) owns levels lg*8 .. lg*8+7 = operand chunks 2lg, 2lg+1
                 float f[16];
-                if (v) {
-                    if (a.pos_gm.interp == 1) lookup8<true, OCT_F16>(&s.lvl[0][lg * 16], a.pos_gm.align_off, a.pos_octs, u, vv, w, f);
-                    else lookup8<false, OCT_F16>(&s.lvl[0][lg * 16], a.pos_gm.align_off, a.pos_octs, u, vv, w, f);
-                }
+                if (v) lookup8o(&s.lvl[0][lg * 16], a.pos_gm.align_off, a.pos_gm.interp == 1, a.pos_octs, u, vv, w, f);
                 else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = 0.f;
@@ -365,10 +368,7 @@ __global__ void __launch_bounds__(HEAD_NT, SPLIT ? 1 : 2) k_head_tc(const __grid
             }
             if (a.amb_octs) {
                 float f[16];
-                if (v) {
-                    if (a.amb_gm.interp == 1) lookup8<true, OCT_F16>(&s.lvl[1][lg * 16], a.amb_gm.align_off, a.amb_octs, u, vv, w, f);
-                    else lookup8<false, OCT_F16>(&s.lvl[1][lg * 16], a.amb_gm.align_off, a.amb_octs, u, vv, w, f);
-                }
+                if (v) lookup8o(&s.lvl[1][lg * 16], a.amb_gm.align_off, a.amb_gm.interp == 1, a.amb_octs, u, vv, w, f);
                 else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = 0.f;

@@ -138,16 +138,14 @@ struct WarpFeed { int next, end; bool dry; };
 
 }  // namespace
 
-// per-frame bias of ambient L0: bias[f][n] = sum_k W[n][32 + k] * cond[f][k]  (the 64 conditioning columns, fp32)
-__global__ void k_amb_frame_bias(const float *__restrict__ w /*[128,96]*/, const float *__restrict__ cond /*[F,64]*/, float *__restrict__ bias) {
-    __shared__ float c[64];
-    const int f = blockIdx.x, n = threadIdx.x;
-    if (n < 64) c[n] = cond[(size_t)f * 64 + n];
-    __syncthreads();
-    float s = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < 64; ++k) s = fmaf(w[n * 96 + 32 + k], c[k], s);
-    bias[(size_t)f * 128 + n] = s;
+// the conditioning vectors of the clip as fp16 operand images: hi = rn16(x), lo = rn16(x - hi)  (64 values = 128 bytes per frame)
+__global__ void k_cond_images(const float *__restrict__ cond /*[F,64]*/, int n, __half *__restrict__ hi, __half *__restrict__ lo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = cond[i];
+    const __half h = __float2half_rn(x);
+    hi[i] = h;
+    lo[i] = __float2half_rn(x - __half2float(h));
 }
 
 template <bool ROBUST>
@@ -193,6 +191,12 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
     if (warp < NWORK) {
         // =====================================================================================================
         // ROW OWNER: thread `row` of slot `s`
+        //
+        // Software-pipelined over the sample sequence of its rays: `cu` is the sample being shaded in this batch, `sl` already
+        // holds the NEXT one.  What happens to the ray after the current sample -- it dies because T < T_thresh (T uses the
+        // weights BEFORE this sample, raymarching.cu:1000-1004), it reaches its sample cap, or marching runs off the volume --
+        // does not depend on the sample's own sigma, so the march to the next sample, the adoption of a new ray and the gather
+        // of the next sample's position features all run in the shadow of the current batch's MMAs.
         // =====================================================================================================
         const int s = warp >> 2, row = tid & (TM - 1);
         unsigned char *h = sm + s * C::SLOT_BYTES, *l = h + 2 * V2_TILE_BYTES, *sht = h + (ROBUST ? 4 : 2) * V2_TILE_BYTES;
@@ -206,8 +210,13 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
         ray_geom_init(sl.g, 0.f, 0.f, 0.f, 1.f, 1.f, 1.f);
         WarpFeed wf{0, 0, false};
         uint32_t dpar = 0, bpar = 0;
-        float sigma = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-        bool have_result = false;
+        bool newray = false;      // sl holds a freshly adopted ray whose SH operand row is not written yet
+        // the sample being shaded: accumulators BEFORE it, its dt / post-sample t, and what happens to its ray afterwards
+        struct { bool valid; int fate, D, gid, frame, nsamp; float dt, t_post, ws, depth, r, g, b, near, far; } cu;
+        cu.valid = false; cu.fate = 0; cu.D = 0; cu.gid = 0; cu.frame = 0; cu.nsamp = 0;
+        cu.dt = cu.t_post = cu.ws = cu.depth = cu.r = cu.g = cu.b = cu.near = cu.far = 0.f;
+        uint32_t feat[16];        // position features of the current sample (packed fp16 pairs), prefetched during the previous batch
+        uint32_t featl[ROBUST ? 16 : 1];
 
 #define ARRIVE_A()                                   \
     do {                                             \
@@ -222,46 +231,17 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
         dpar ^= 1u;                                  \
         fence_after_sync();                          \
     } while (0)
+        // optional phase stamps (thread 0 = row 0 of slot 0 of every CTA): cycles between consecutive PH() points
+        long long ph_last = clock64();
+#define PH(i)                                                                              \
+    if (a.phase_cycles && tid == 0) {                                                      \
+        const long long now_ = clock64();                                                  \
+        atomicAdd(a.phase_cycles + (i), (unsigned long long)(now_ - ph_last));             \
+        ph_last = now_;                                                                    \
+    }
 
-        for (;;) {
-            // ---------------- ray work: composite the sample just shaded, march on, refill (raymarching.cu:942-1029, :827-929) --------
-            if (have_result && sl.active) {
-                const float alpha = 1.0f - expf(-sigma * sl.dt);
-                const float T = 1.0f - sl.ws;
-                const float wgt = alpha * T;
-                sl.ws += wgt;
-                sl.depth += wgt * sl.t;  // sl.t is already the post-sample t (deltas[1])
-                sl.r += wgt * cr;
-                sl.gch += wgt * cg;
-                sl.b += wgt * cb;
-                sl.nsamp += 1;
-                if (a.valid_samples) warp_agg_add(a.valid_samples, sl.frame, 1);
-                int D = 0;  // death index (1-based sample position), 0 = still alive
-                bool suspend = false;
-                if (T < a.T_thresh) D = sl.nsamp;
-                else if (sl.nsamp >= sl.cap) suspend = true;
-                else if (!march_next(mc, sl.g, sl.far_m, sl.t, sl.px, sl.py, sl.pz, sl.dt)) D = sl.nsamp + 1;
-                if (D) {
-                    finalize_ray(a, sl, true);
-                    if (a.pass == 1) warp_agg_add(a.hist, sl.frame * (a.max_steps + 2) + D, 1);
-                    sl.active = false;
-                } else if (suspend) {
-                    if (a.pass == 1) {
-                        finalize_ray(a, sl, false);  // raw depth: pass 2 keeps accumulating
-                        a.rays_t[sl.gid] = sl.t;
-                        cg::coalesced_group grp = cg::coalesced_threads();
-                        int base = 0;
-                        if (grp.thread_rank() == 0) base = atomicAdd(a.n_survivors, (int)grp.size());
-                        base = grp.shfl(base, 0);
-                        a.survivors[base + grp.thread_rank()] = sl.gid;
-                    } else {
-                        finalize_ray(a, sl, true);
-                    }
-                    sl.active = false;
-                }
-            }
-            __syncwarp();
-            // refill dead lanes from the warp's feed
+        // refill dead lanes of `sl` from the warp's feed (all lanes of the warp, converged)
+        auto refill = [&]() {
 #pragma unroll 1
             for (int tries = 0; tries < 4; ++tries) {
                 const unsigned need = __ballot_sync(0xffffffffu, !sl.active);
@@ -310,17 +290,49 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
                         if (!live) finalize_ray(a, sl, true);
                     }
                     sl.active = live;
-                    if (live) {   // SH(dir) is constant along the ray: its K16 operand row is written once, at adoption (shencoder.cu:43-68)
-                        float shv[16];
-                        sh4(sl.g.dx, sl.g.dy, sl.g.dz, shv);
-                        store_chunk<false, false>(sht, sht, k16_off(row, 0), &shv[0]);
-                        store_chunk<false, false>(sht, sht, k16_off(row, 1), &shv[8]);
-                    }
+                    newray = live;
                 }
                 __syncwarp();
             }
-            const bool valid = sl.active;
-            have_result = true;
+        };
+        // eight levels [8 * half, 8 * half + 8) of the position grid at the NEXT sample -> feat / featl
+        auto prefetch_pos = [&](int half) {
+            float f[16];
+            if (sl.active) {
+                const float inv2b = 2.0f * mc.bound;
+                const float u = __fdiv_rn(__fadd_rn(sl.px, mc.bound), inv2b), vv = __fdiv_rn(__fadd_rn(sl.py, mc.bound), inv2b),
+                            w = __fdiv_rn(__fadd_rn(sl.pz, mc.bound), inv2b);
+                lookup8<ROBUST ? OCT_I16 : OCT_F16>(&ms.lvl[0][half * 16], a.pos_gm.align_off, smooth_p, a.pos_octs, u, vv, w, f);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t hi = pack2<false>(f[2 * i], f[2 * i + 1]);
+                feat[half * 8 + i] = hi;
+                if (ROBUST) {
+                    const float2 b = unpack_h2(hi);
+                    featl[half * 8 + i] = pack2<false>(f[2 * i] - b.x, f[2 * i + 1] - b.y);
+                }
+            }
+        };
+        // make `cu` the sample `sl` points at
+        auto rotate = [&]() {
+            cu.valid = sl.active;
+            cu.dt = sl.dt; cu.t_post = sl.t;
+            cu.ws = sl.ws; cu.depth = sl.depth; cu.r = sl.r; cu.g = sl.gch; cu.b = sl.b;
+            cu.gid = sl.gid; cu.frame = sl.frame; cu.near = sl.near; cu.far = sl.far; cu.nsamp = sl.nsamp;
+        };
+
+        // ---------------- prologue: first rays, first samples, their position features ----------------
+        refill();
+        prefetch_pos(0);
+        prefetch_pos(1);
+        rotate();
+
+        for (;;) {
+            const bool valid = cu.valid;
             {   // batch accounting: this warp's "live rows" flag, then the split-phase batch barrier
                 const unsigned any = __ballot_sync(0xffffffffu, valid);
                 if (lane == 0) {
@@ -328,43 +340,59 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
                     mbar_arrive(&ms.batch_bar);
                 }
             }
-
-            // ---------------- position grid -> h0 k[0,32) (and its residual image in robust mode) ----------------
-            uint32_t pos16[16];
-            {
-                float u = 0.f, vv = 0.f, w = 0.f;
-                if (valid) {
-                    const float inv2b = 2.0f * mc.bound;
-                    u = __fdiv_rn(__fadd_rn(sl.px, mc.bound), inv2b);
-                    vv = __fdiv_rn(__fadd_rn(sl.py, mc.bound), inv2b);
-                    w = __fdiv_rn(__fadd_rn(sl.pz, mc.bound), inv2b);
-                }
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    float f[16];
-                    if (valid) {
-                        if (smooth_p) lookup8<true, ROBUST ? OCT_I16 : OCT_F16>(&ms.lvl[0][half * 16], a.pos_gm.align_off, a.pos_octs, u, vv, w, f);
-                        else lookup8<false, ROBUST ? OCT_I16 : OCT_F16>(&ms.lvl[0][half * 16], a.pos_gm.align_off, a.pos_octs, u, vv, w, f);
-                    } else {
+            // ---------------- ambient-net input: h0 k[0,32) <- position features, k[32,64) | h1 k[0,32) <- conditioning ----------------
+            if (newray && valid) {   // SH(dir) is constant along the ray: its K16 operand row is written once per ray (shencoder.cu:43-68)
+                float shv[16];
+                sh4(sl.g.dx, sl.g.dy, sl.g.dz, shv);
+                store_chunk<false, false>(sht, sht, k16_off(row, 0), &shv[0]);
+                store_chunk<false, false>(sht, sht, k16_off(row, 1), &shv[8]);
+                newray = false;
+            }
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) f[i] = 0.f;
-                    }
-                    put8<false, ROBUST>(h, l, row, 2 * half, &f[0]);
-                    put8<false, ROBUST>(h, l, row, 2 * half + 1, &f[8]);
+            for (int c = 0; c < 4; ++c) {
+                *reinterpret_cast<uint4 *>(h + sw128_off(row, c)) = make_uint4(feat[4 * c], feat[4 * c + 1], feat[4 * c + 2], feat[4 * c + 3]);
+                if (ROBUST) *reinterpret_cast<uint4 *>(l + sw128_off(row, c)) = make_uint4(featl[4 * c], featl[4 * c + 1], featl[4 * c + 2], featl[4 * c + 3]);
+            }
+            {   // the frame's conditioning vector as pre-rounded fp16 images (k_cond_images): 8 x 16 bytes straight into the operand tiles
+                const uint4 *ch = reinterpret_cast<const uint4 *>(t.cond_hi) + (size_t)cu.frame * 8;
+                const uint4 *cl = reinterpret_cast<const uint4 *>(t.cond_lo) + (size_t)cu.frame * 8;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) pos16[half * 8 + i] = pack2<false>(f[2 * i], f[2 * i + 1]);
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t off = (c < 4) ? sw128_off(row, 4 + c) : (uint32_t)V2_TILE_BYTES + sw128_off(row, c - 4);
+                    *reinterpret_cast<uint4 *>(h + off) = __ldg(ch + c);
+                    if (ROBUST) *reinterpret_cast<uint4 *>(l + off) = __ldg(cl + c);
                 }
             }
+            PH(0)   // operand rows of ambient L0
             ARRIVE_A();   // -> ambient L0
+
+            // ---------------- in the shadow of the ambient net: fate of the ray, march to the next sample, refill ----------------
+            if (valid) {
+                const int ns = cu.nsamp + 1;                 // samples composited once this one is
+                const float T = 1.0f - cu.ws;
+                if (T < a.T_thresh) { cu.fate = 1; cu.D = ns; }
+                else if (ns >= sl.cap) cu.fate = 2;
+                else if (!march_next(mc, sl.g, sl.far_m, sl.t, sl.px, sl.py, sl.pz, sl.dt)) { cu.fate = 1; cu.D = ns + 1; }
+                else { cu.fate = 0; sl.nsamp = ns; }
+                if (cu.fate) sl.active = false;
+            }
+            __syncwarp();
+            refill();
+            PH(1)   // fate + march + refill
 
             // ---------------- ambient net 96 -> 128 -> 128 -> 3 (radnerf.py:121) ----------------
             WAIT_D();
-            epilogue_row<true, 1, ROBUST>(taddr, h, l, row, t.amb_bias + (size_t)sl.frame * 128);
+            PH(2)   // wait: ambient L0
+            epilogue_row<true, 0, ROBUST>(taddr, h, l, row, nullptr);
             ARRIVE_A();   // -> ambient L1
+            PH(3)   // epilogue: ambient L0
             WAIT_D();
+            PH(4)   // wait: ambient L1
             epilogue_row<true, 0, ROBUST>(taddr, h, l, row, nullptr);
             ARRIVE_A();   // -> ambient out (N = 16)
+            PH(5)   // epilogue: ambient L1
             WAIT_D();
+            PH(6)   // wait: ambient out
             float amb0, amb1, amb2;
             {
                 float o[16];
@@ -382,13 +410,12 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
                 }
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<uint4 *>(h + sw128_off(row, c)) = make_uint4(pos16[4 * c], pos16[4 * c + 1], pos16[4 * c + 2], pos16[4 * c + 3]);
+                    *reinterpret_cast<uint4 *>(h + sw128_off(row, c)) = make_uint4(feat[4 * c], feat[4 * c + 1], feat[4 * c + 2], feat[4 * c + 3]);
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     float f[16];
                     if (valid) {
-                        if (smooth_a) lookup8<true, OCT_F16>(&ms.lvl[1][half * 16], a.amb_gm.align_off, a.amb_octs, u, vv, w, f);
-                        else lookup8<false, OCT_F16>(&ms.lvl[1][half * 16], a.amb_gm.align_off, a.amb_octs, u, vv, w, f);
+                        lookup8<OCT_F16>(&ms.lvl[1][half * 16], a.amb_gm.align_off, smooth_a, a.amb_octs, u, vv, w, f);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) f[i] = 0.f;
@@ -397,16 +424,28 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
                     put8<false, false>(h, h, row, 4 + 2 * half + 1, &f[8]);
                 }
             }
+            PH(7)   // tanh + ambient gather
             ARRIVE_A();   // -> sigma L0
 
-            // ---------------- sigma net 64 -> 128 -> 128 -> (128 geo + sigma) (radnerf.py:127-130) ----------------
+            // ---------------- sigma net 64 -> 128 -> 128 -> (128 geo + sigma) (radnerf.py:127-130); in its shadow: the NEXT sample's
+            //                  position features (the current ones are in the operand tile now) ----------------
+            prefetch_pos(0);
+            PH(8)   // prefetch: position levels 0-7 of the next sample
             WAIT_D();
+            PH(9)   // wait: sigma L0
             epilogue_row<true, 0, false>(taddr, h, h, row, nullptr);
             ARRIVE_A();   // -> sigma L1
+            PH(10)  // epilogue: sigma L0
+            prefetch_pos(1);
+            PH(11)  // prefetch: position levels 8-15 of the next sample
             WAIT_D();
+            PH(12)  // wait: sigma L1
             epilogue_row<true, 0, false>(taddr, h, h, row, nullptr);
             ARRIVE_A();   // -> sigma L2 (geo rows + the sigma row as an N = 16 group)
+            PH(13)  // epilogue: sigma L1
             WAIT_D();
+            PH(14)  // wait: sigma L2
+            float sigma;
             {
                 float o[16];
                 tmem_ld16(taddr + 128u, o);
@@ -415,12 +454,17 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             }
             epilogue_row<false, 0, false>(taddr, h, h, row, nullptr);   // geo features (no activation) -> color-net input
             ARRIVE_A();   // -> color L0 (geo K = 128 + SH K = 16)
+            PH(15)  // epilogue: sigma L2 (sigma + geo)
 
             // ---------------- color net (16 SH + 128 geo [+ folded individual code]) -> 128 -> 3 (radnerf.py:137-141) ----------------
             WAIT_D();
+            PH(16)  // wait: color L0
             epilogue_row<true, 2, false>(taddr, h, h, row, ms.cbias);
             ARRIVE_A();   // -> color out (N = 16)
+            PH(17)  // epilogue: color L0
             WAIT_D();
+            PH(18)  // wait: color out
+            float cr, cg, cb;
             {
                 float o[16];
                 tmem_ld16(taddr + 128u, o);
@@ -431,6 +475,41 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             }
             fence_before_sync();   // the next batch's MMAs overwrite these TMEM columns: order the loads above before the next arrive
 
+            // ---------------- composite the sample (raymarching.cu:978-1006) and retire / suspend / continue its ray ----------------
+            if (valid) {
+                const float alpha = 1.0f - expf(-sigma * cu.dt);
+                const float T = 1.0f - cu.ws;
+                const float wgt = alpha * T;
+                cu.ws += wgt;
+                cu.depth += wgt * cu.t_post;   // deltas[1]: t after the sample
+                cu.r += wgt * cr;
+                cu.g += wgt * cg;
+                cu.b += wgt * cb;
+                if (a.valid_samples) warp_agg_add(a.valid_samples, cu.frame, 1);
+                if (cu.fate == 0) {            // same ray goes on: `sl` (already at its next sample) takes the accumulators
+                    sl.ws = cu.ws; sl.depth = cu.depth; sl.r = cu.r; sl.gch = cu.g; sl.b = cu.b;
+                } else {
+                    const size_t g = (size_t)cu.gid;
+                    const bool normalise = cu.fate == 1 || a.pass != 1;   // a suspended pass-1 ray keeps its raw depth: pass 2 goes on accumulating
+                    a.image[3 * g] = cu.r; a.image[3 * g + 1] = cu.g; a.image[3 * g + 2] = cu.b;
+                    a.wsum[g] = cu.ws;
+                    // renderer.py:394: depth = clamp(depth - nears, min=0) / (fars - nears)
+                    a.depth[g] = normalise ? __fdiv_rn(fmaxf(__fsub_rn(cu.depth, cu.near), 0.f), __fsub_rn(cu.far, cu.near)) : cu.depth;
+                    if (cu.fate == 1) {
+                        if (a.pass == 1) warp_agg_add(a.hist, cu.frame * (a.max_steps + 2) + cu.D, 1);
+                    } else if (a.pass == 1) {
+                        a.rays_t[g] = cu.t_post;
+                        cg::coalesced_group grp = cg::coalesced_threads();
+                        int base = 0;
+                        if (grp.thread_rank() == 0) base = atomicAdd(a.n_survivors, (int)grp.size());
+                        base = grp.shfl(base, 0);
+                        a.survivors[base + grp.thread_rank()] = cu.gid;
+                    }
+                }
+            }
+            __syncwarp();
+            rotate();
+
             // ---------------- end of batch: was anything alive in it? ----------------
             mbar_wait(&ms.batch_bar, bpar);
             int any = 0;
@@ -438,8 +517,11 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             for (int i = 0; i < NWORK; ++i) any |= ms.flag[bpar][i];
             bpar ^= 1u;
             __syncwarp();
+            PH(19)  // sigmoid + composite + end-of-batch check
+            if (a.phase_cycles && tid == 0) atomicAdd(a.phase_cycles + 31, 1ull);   // batches
             if (!any) break;
         }
+#undef PH
 #undef ARRIVE_A
 #undef WAIT_D
     } else if (warp == NWORK) {
@@ -471,6 +553,28 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             __syncwarp();
             wc += n;
         };
+        // one 128-wide ambient layer in the split arithmetic: two K tiles, each as (hi, lo) weight images shared by all slots;
+        // D = Al*Wh + Ah*Wl + Ah*Wh, small terms first
+        auto robust_layer = [&](int ks0, int ks1) {
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                const uint32_t wh = tile(0), wl = tile(1);
+                const int ks = kt ? ks1 : ks0;
+                fence_after_sync();
+#pragma unroll
+                for (int s = 0; s < NSLOT; ++s) {
+                    if (kt == 0) { mbar_wait(&ms.a_ready[s], apar); fence_after_sync(); }
+                    if (elect_one()) {
+                        mma_sw(d_of(s), l_of(s, kt), wh, ks, idesc128, kt ? 1u : 0u);
+                        mma_sw(d_of(s), h_of(s, kt), wl, ks, idesc128, 1u);
+                        mma_sw(d_of(s), h_of(s, kt), wh, ks, idesc128, 1u);
+                        if (kt == 1) mma_commit(&ms.d_ready[s]);
+                    }
+                    __syncwarp();
+                }
+                release(2);
+            }
+        };
 #define SLOT_BEGIN(sv)                            \
     mbar_wait(&ms.a_ready[sv], apar);             \
     fence_after_sync();                           \
@@ -481,25 +585,22 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
     __syncwarp();
 
         for (;;) {
-            // ---- ambient L0: K = 32 position features (conditioning folded into the epilogue bias) ----
-            {
-                const uint32_t w0 = tile(0), w0l = ROBUST ? tile(1) : 0u;
+            // ---- ambient L0: K = 96 = 32 position features + 64 conditioning values (h0 k[0,64), h1 k[0,32)) ----
+            if (ROBUST) {
+                robust_layer(4, 2);
+            } else {
+                const uint32_t w0 = tile(0), w1 = tile(1);
                 fence_after_sync();
 #pragma unroll
                 for (int s = 0; s < NSLOT; ++s) {
                     SLOT_BEGIN(s)
-                    if (ROBUST) {   // small terms first
-                        mma_sw(d_of(s), l_of(s, 0), w0, 2, idesc128, 0u);
-                        mma_sw(d_of(s), h_of(s, 0), w0l, 2, idesc128, 1u);
-                        mma_sw(d_of(s), h_of(s, 0), w0, 2, idesc128, 1u);
-                    } else {
-                        mma_sw(d_of(s), h_of(s, 0), w0, 2, idesc128, 0u);
-                    }
+                    mma_sw(d_of(s), h_of(s, 0), w0, 4, idesc128, 0u);
+                    mma_sw(d_of(s), h_of(s, 1), w1, 2, idesc128, 1u);
                     SLOT_END(s)
                 }
-                release(ROBUST ? 2 : 1);
-                apar ^= 1u;
+                release(2);
             }
+            apar ^= 1u;
             // everyone has arrived for this batch: is anything alive in it?  (read now, acted upon at the end of the batch)
             mbar_wait(&ms.batch_bar, bpar);
             int any = 0;
@@ -508,24 +609,7 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             bpar ^= 1u;
             // ---- ambient L1: K = 128 ----
             if (ROBUST) {
-#pragma unroll
-                for (int kt = 0; kt < 2; ++kt) {   // two half-layers, each (hi, lo) weight tiles for all slots
-                    const uint32_t wh = tile(0), wl = tile(1);
-                    fence_after_sync();
-#pragma unroll
-                    for (int s = 0; s < NSLOT; ++s) {
-                        if (kt == 0) { mbar_wait(&ms.a_ready[s], apar); fence_after_sync(); }
-                        if (elect_one()) {
-                            mma_sw(d_of(s), l_of(s, kt), wh, 4, idesc128, kt ? 1u : 0u);
-                            mma_sw(d_of(s), h_of(s, kt), wl, 4, idesc128, 1u);
-                            mma_sw(d_of(s), h_of(s, kt), wh, 4, idesc128, 1u);
-                            if (kt == 1) mma_commit(&ms.d_ready[s]);
-                        }
-                        __syncwarp();
-                    }
-                    release(2);
-                }
-                apar ^= 1u;
+                robust_layer(4, 4);
             } else {
                 const uint32_t w0 = tile(0), w1 = tile(1);
                 fence_after_sync();
@@ -537,8 +621,8 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
                     SLOT_END(s)
                 }
                 release(2);
-                apar ^= 1u;
             }
+            apar ^= 1u;
             // ---- ambient out: N = 16 group from the resident tiles, into columns 128..143 ----
 #pragma unroll
             for (int s = 0; s < NSLOT; ++s) {
@@ -665,8 +749,9 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
 
 size_t head_v2_smem_bytes(bool robust) { return robust ? smem_bytes<true>() : smem_bytes<false>(); }
 
-cudaError_t launch_amb_frame_bias(const float *w_amb0, const float *cond_feat, int n_frames, float *bias, cudaStream_t st) {
-    k_amb_frame_bias<<<n_frames, 128, 0, st>>>(w_amb0, cond_feat, bias);
+cudaError_t launch_cond_images(const float *cond_feat, int n_frames, void *cond_hi, void *cond_lo, cudaStream_t st) {
+    const int n = n_frames * 64;
+    k_cond_images<<<(n + 255) / 256, 256, 0, st>>>(cond_feat, n, (__half *)cond_hi, (__half *)cond_lo);
     return cudaGetLastError();
 }
 
