@@ -111,7 +111,7 @@ class ClockSampler:
 
 _CPU_THREADS = None
 DEFAULT_PRECISION = "fp16"                 # the headline mode of this bench
-SMOKE_PRECISIONS = ("fp16",)               # what __graft_entry__.smoke() renders beside the fp32 kernels
+SMOKE_PRECISIONS = ("fp16", "robust")              # what __graft_entry__.smoke() renders beside the fp32 kernels
 
 
 def metric_name(args):
@@ -119,7 +119,7 @@ def metric_name(args):
     return f"frames/sec at {args.size}x{args.size} " + ("head" if args.head_only else "head+torso")
 
 
-def cpu_reference_fps(args, n_frames, keep_images=False):
+def cpu_reference_fps(args, n_frames, keep_images=False, rays=None):
     """The reference's path on the host cores: the reference's PyTorch-eager modules restated in oracle/render.py
     over the C restatement of its CUDA-only native ops (kind "port": the reference has no CPU implementation of
     those ops and its Python cannot travel to the GPU box).  All host threads."""
@@ -154,7 +154,10 @@ def cpu_reference_fps(args, n_frames, keep_images=False):
     imgs, knife = [], []
     for t in range(n_frames):
         fi = sc.frame_inputs(t)
-        out = orc.render(fi["rays_o"], fi["rays_d"], fi["cond"], fi["bg_coords"], fi["poses"], bg_color=fi["bg_color"],
+        # `rays`: ([F,N,3], [F,N,3]) CPU tensors to render instead of torch get_rays' -- the parity leg hands over the rays the GPU
+        # path generated in-kernel, so that both sides see IDENTICAL rays (they differ from get_rays' by <= 2 ulp)
+        ro, rd = (fi["rays_o"], fi["rays_d"]) if rays is None else (rays[0][t].view(1, -1, 3), rays[1][t].view(1, -1, 3))
+        out = orc.render(ro, rd, fi["cond"], fi["bg_coords"], fi["poses"], bg_color=fi["bg_color"],
                          T_thresh=sc.T_thresh, **sc.hparams)
         S += out["stats"]["S"]
         if keep_images:
@@ -395,21 +398,23 @@ def _main(args, out):
     cpu = None
     parity = None
     if rank == 0 and not args.no_cpu_baseline:
-        v, cores, dt, _, ref_img, ref_knife = cpu_reference_fps(args, args.cpu_frames, keep_images=True)
+        Fp = args.cpu_frames
+        kro, krd = model.generate_rays(poses_dev[:Fp], sc.intrinsics, H, W)      # the rays the clip path generates in-kernel
+        v, cores, dt, _, ref_img, ref_knife = cpu_reference_fps(args, args.cpu_frames, keep_images=True, rays=(kro.cpu(), krd.cpu()))
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "port",
                "sample": f"{args.cpu_frames} frame(s) of the same clip at {H}x{W} ({dt:.1f} s)",
                "note": "oracle/render.py + oracle/native_ops.c on the host cores (the reference's Python has no CPU path for its native ops "
                        "and does not travel to this box); `cores` = calibrated thread count, `host_cores` = os.cpu_count()"}
         # parity of the BENCHMARKED configuration: the same frames through the timed path (clip API, in-kernel rays, timed
         # precision) against the fp32 CPU oracle's frames just rendered for the baseline (max-abs 1e-3 / PSNR 50 dB)
-        Fp = args.cpu_frames
         mine = model.render_clip(poses_dev[:Fp], sc.intrinsics, H, W, cond_feat=model.cal_cond_feat_clip(cond_dev)[s:s + Fp],
                                  bg_color=bg_color, bg_coords=bg_coords, pose6=pose6_dev[:Fp] if not args.head_only else None,
                                  T_thresh=sc.T_thresh, frames_per_call=args.frames_per_call).float().cpu()
         d = (mine - ref_img).abs().max(-1).values                       # [F,N]
         knife = ref_knife < 1e-3                                         # rays whose termination an fp32 reordering may flip
         mse = ((mine.double() - ref_img.double()) ** 2).mean().item()
-        parity = {"vs": "fp32 CPU oracle (oracle/render.py), identical poses / conditioning; rays generated in-kernel vs torch get_rays",
+        parity = {"vs": "fp32 CPU oracle (oracle/render.py) on IDENTICAL rays (the in-kernel generated ones, exported through gfpp_debug_generate_rays: "
+                        "<= 2 ulp from torch get_rays) and identical conditioning",
                   "precision": args.precision, "frames": Fp, "size": H,
                   "max_abs": d[~knife].max().item(), "max_abs_all": d.max().item(), "n_knife": int(knife.sum()),
                   "n_over_1e-3": int((d > 1e-3).sum()), "n_pixels": d.numel(),

@@ -64,7 +64,7 @@ EXPORTS = [
     "gfpp_last_error", "gfpp_version", "gfpp_check_device", "gfpp_near_far_from_aabb", "gfpp_march_rays",
     "gfpp_composite_rays", "gfpp_grid_encode_forward", "gfpp_sh_encode_forward", "gfpp_freq_encode_forward",
     "gfpp_model_packed_bytes", "gfpp_model_pack", "gfpp_render_workspace_bytes", "gfpp_render_frames",
-    "gfpp_last_launch_count", "gfpp_profile_enable", "gfpp_profile_read", "gfpp_profile_phases", "gfpp_tc_selftest",
+    "gfpp_last_launch_count", "gfpp_profile_enable", "gfpp_profile_read", "gfpp_profile_phases", "gfpp_tc_selftest", "gfpp_debug_generate_rays",
 ]
 
 
@@ -94,6 +94,7 @@ def lib():
         L.gfpp_sh_encode_forward.argtypes = [c_void_p, c_void_p, c_u32, c_u32, c_u32, c_void_p]
         L.gfpp_freq_encode_forward.argtypes = [c_void_p, c_u32, c_u32, c_u32, c_u32, c_void_p, c_void_p]
         L.gfpp_profile_phases.argtypes = [c_void_p]
+        L.gfpp_debug_generate_rays.argtypes = [c_void_p, c_u32, c_f, c_f, c_f, c_f, c_u32, c_u32, c_void_p, c_void_p, c_void_p]
         L.gfpp_tc_selftest.argtypes = [c_void_p, c_void_p, c_u32, c_u32, c_int, c_int, c_void_p, c_void_p, c_void_p]
         _lib = L
     return _lib

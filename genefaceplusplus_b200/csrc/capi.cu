@@ -560,6 +560,19 @@ int gfpp_model_pack(const gfpp_model_desc *d, void *packed, size_t packed_bytes,
     return GFPP_OK;
 }
 
+int gfpp_debug_generate_rays(const float *poses_c2w, uint32_t n_frames, float fx, float fy, float cx, float cy, uint32_t img_h,
+                             uint32_t img_w, float *rays_o, float *rays_d, void *stream) {
+    if (!poses_c2w || !rays_o || !rays_d || n_frames == 0 || img_h == 0 || img_w == 0)
+        return fail(GFPP_ERR_INVALID, "debug_generate_rays: null pointer or empty image%s");
+    HeadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_frames = (int)n_frames; a.n_rays = (int)(img_h * img_w);
+    a.poses = poses_c2w; a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.img_w = (int)img_w;
+    g_launches = 0;
+    CK(launch_dump_rays(a, rays_o, rays_d, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
 size_t gfpp_render_workspace_bytes(uint32_t n_frames, uint32_t n_rays, uint32_t max_steps) {
     return work_layout(n_frames, n_rays, max_steps).total;
 }

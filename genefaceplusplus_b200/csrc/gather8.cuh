@@ -35,9 +35,9 @@ __device__ __forceinline__ float2 unpack_i16x2(uint32_t w) {
     return make_float2(lo - 12615680.0f, hi - 12615680.0f);   // 12582912 + 32768
 }
 
-template <int FMT>
-__device__ __forceinline__ void lookup8(const uint4 *lvl, float align_off, bool smooth, const uint4 *__restrict__ octs, float u, float v, float w,
-                                        float (&f)[16]) {
+template <int FMT, bool SMOOTH>
+__device__ __forceinline__ void lookup8_impl(const uint4 *lvl, float align_off, const uint4 *__restrict__ octs, float u, float v, float w,
+                                             float (&f)[16]) {
     float fx[8], fy[8], fz[8];
     uint4 lo4[8], hi4[8];
 #pragma unroll
@@ -48,7 +48,7 @@ __device__ __forceinline__ void lookup8(const uint4 *lvl, float align_off, bool 
               pz = __fadd_rn(__fmul_rn(w, s), align_off);
         const float x0 = floorf(px), y0 = floorf(py), z0 = floorf(pz);
         px -= x0; py -= y0; pz -= z0;
-        if (smooth) {   // warp-uniform
+        if (SMOOTH) {
             px = px * px * (3.0f - 2.0f * px);
             py = py * py * (3.0f - 2.0f * py);
             pz = pz * pz * (3.0f - 2.0f * pz);
@@ -83,6 +83,13 @@ __device__ __forceinline__ void lookup8(const uint4 *lvl, float align_off, bool 
 #pragma unroll
         for (int i = 0; i < 16; ++i) f[i] = 0.f;
     }
+}
+
+template <int FMT>
+__device__ __forceinline__ void lookup8(const uint4 *lvl, float align_off, bool smooth, const uint4 *__restrict__ octs, float u, float v, float w,
+                                        float (&f)[16]) {
+    if (smooth) lookup8_impl<FMT, true>(lvl, align_off, octs, u, v, w, f);   // warp-uniform: only one instantiation ever runs (I-cache)
+    else lookup8_impl<FMT, false>(lvl, align_off, octs, u, v, w, f);
 }
 
 }  // namespace gfpp

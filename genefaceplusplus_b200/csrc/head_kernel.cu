@@ -435,6 +435,22 @@ __global__ void k_schedule(const int *__restrict__ hist, int n_frames, int n_ray
     B_total[f] = cum;
 }
 
+// debug: the rays the fused path generates in-kernel (load_ray, head_common.cuh) written out like get_rays would (utils.py:352-360)
+__global__ void k_dump_rays(const __grid_constant__ HeadArgs a, float *__restrict__ rays_o, float *__restrict__ rays_d) {
+    const int total = a.n_frames * a.n_rays;
+    for (int gid = blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += gridDim.x * blockDim.x) {
+        const int f = gid / a.n_rays;
+        RayGeom g;
+        load_ray(a, f, gid - f * a.n_rays, g);
+        rays_o[3 * (size_t)gid] = g.ox; rays_o[3 * (size_t)gid + 1] = g.oy; rays_o[3 * (size_t)gid + 2] = g.oz;
+        rays_d[3 * (size_t)gid] = g.dx; rays_d[3 * (size_t)gid + 1] = g.dy; rays_d[3 * (size_t)gid + 2] = g.dz;
+    }
+}
+cudaError_t launch_dump_rays(const HeadArgs &a, float *rays_o, float *rays_d, cudaStream_t st) {
+    k_dump_rays<<<grid_for((uint64_t)a.n_frames * a.n_rays, 256), 256, 0, st>>>(a, rays_o, rays_d);
+    return cudaGetLastError();
+}
+
 size_t head_smem_bytes() { return sizeof(Smem); }
 
 cudaError_t launch_head(const HeadArgs &a, int total_hint, cudaStream_t st) {

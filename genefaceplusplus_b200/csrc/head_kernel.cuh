@@ -96,6 +96,7 @@ size_t head_v2_smem_bytes(bool robust);
 size_t head_smem_bytes();
 cudaError_t launch_head(const HeadArgs &a, int total_hint, cudaStream_t st);
 cudaError_t launch_ray_setup(const HeadArgs &a, cudaStream_t st);
+cudaError_t launch_dump_rays(const HeadArgs &a, float *rays_o, float *rays_d, cudaStream_t st);
 cudaError_t launch_schedule(const int *hist, int n_frames, int n_rays, int max_steps, int *B_total, cudaStream_t st);
 
 }  // namespace gfpp

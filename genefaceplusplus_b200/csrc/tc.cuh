@@ -47,6 +47,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
             : "memory");
     } while (!ok);
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // plain arrive (count 1) by the executing thread; release semantics at CTA scope
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

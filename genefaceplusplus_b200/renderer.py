@@ -416,6 +416,21 @@ class RADNeRF(nn.Module):
         del hold
         return res
 
+    def generate_rays(self, poses_c2w, intrinsics, H, W):
+        """The rays the clip path generates in-kernel, written out (debug / tests): ([F,H*W,3], [F,H*W,3]) on the model's device."""
+        dev = self.density_bitfield.device
+        if dev.type != "cuda":
+            raise _capi.GfppError("model is not on a CUDA device: libgfpp has no CPU path (call .cuda())")
+        poses = poses_c2w.to(dev, torch.float32).reshape(-1, 16).contiguous()
+        Fn = poses.shape[0]
+        ro = torch.empty(Fn, H * W, 3, device=dev, dtype=torch.float32)
+        rd = torch.empty_like(ro)
+        fx, fy, cx, cy = [float(v) for v in intrinsics]
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().gfpp_debug_generate_rays(poses.data_ptr(), Fn, fx, fy, cx, cy, H, W, ro.data_ptr(), rd.data_ptr(),
+                                                           _capi.stream_ptr(dev)), "gfpp_debug_generate_rays")
+        return ro, rd
+
     # ------------------------------------------------------------------ the reference's render()
     @torch.no_grad()
     def render(self, rays_o, rays_d, cond, bg_coords, poses, index=0, dt_gamma=0, bg_color=None, perturb=False,

@@ -203,6 +203,11 @@ GFPP_API int gfpp_profile_phases(void *dev_u64x32);
  * N <= 144, K <= 144.  precision: 1 = fp16, 2 = bf16 hi/lo split (3 MMAs), 3 = bf16.  scratch: >= 6*18432 bytes. */
 GFPP_API int gfpp_tc_selftest(const float *A, const float *W, uint32_t N, uint32_t K, int k16_tail, int precision,
                               void *scratch, float *out, void *stream);
+/* Debug / test hook: write out the rays the fused path generates IN-KERNEL from poses + intrinsics (pixel centres, normalised,
+ * rotated by c2w[:3,:3]: modules/radnerfs/utils.py:302-360), [F, img_h*img_w, 3] each, so that tests can measure their distance to
+ * torch get_rays and hand exactly these rays to the oracle. */
+GFPP_API int gfpp_debug_generate_rays(const float *poses_c2w, uint32_t n_frames, float fx, float fy, float cx, float cy,
+                                      uint32_t img_h, uint32_t img_w, float *rays_o, float *rays_d, void *stream);
 /* number of kernels the last gfpp_render_frames call on this thread launched */
 GFPP_API int gfpp_last_launch_count(void);
 

@@ -27,7 +27,7 @@ def _both(sc, state, t, precision):
     return ref, out
 
 
-@pytest.mark.parametrize("precision", ["fp16", "bf16x3", "bf16"])
+@pytest.mark.parametrize("precision", ["fp16", "robust", "bf16x3", "bf16"])
 @pytest.mark.parametrize("torso,ds", [(False, 1.0), (True, 8.0), (False, 64.0)])
 def test_default_scene_all_modes_pass(oracle_ops, precision, torso, ds):
     sc = scn.Scene(H=64, W=64, T=4, torso=torso, density_scale=ds)
