@@ -258,6 +258,8 @@ def _main(args, out):
     u8_host = torch.empty(T * world if rank == 0 else 1, N, 3, dtype=torch.uint8).pin_memory()
     launches = 0
 
+    og = gdist.OverlappedGather(T, (N, 3), torch.uint8, dev) if world > 1 else None
+
     def step_device():
         nonlocal launches
         feat = model.cal_cond_feat_clip(cond_dev)[s:e]
@@ -273,9 +275,11 @@ def _main(args, out):
                                       **({"u8_out": u8[a:b]} if world > 1 else {"rgb_out": rgb[a:b]}))
             stats_acc.append(res["stats"])
             n0 += model.last_launch_count
+            if world > 1:
+                og.push(u8, a, b)          # this chunk's uint8 frames go out over NVLink while the next chunk renders
         launches += n0
         if world > 1:
-            return gdist.gather_frames(u8, T * world)
+            return og.finish()
         return rgb
 
     def step_e2e():
@@ -286,10 +290,16 @@ def _main(args, out):
         c = cond_host.to(dev, non_blocking=True)
         p6 = scn.convert_poses(poses_host).to(dev, non_blocking=True) if not args.head_only else None
         cf = model.cal_cond_feat_clip(c)[s:e]
-        out = model.render_clip(p, sc.intrinsics, H, W, cond_feat=cf, bg_color=bg_color, bg_coords=bg_coords, pose6=p6,
-                                T_thresh=sc.T_thresh, frames_per_call=args.frames_per_call, out=u8, as_uint8=True)
         if world > 1:
-            out = gdist.gather_frames(out, T * world)
+            for a in range(0, T, args.frames_per_call):
+                b = min(T, a + args.frames_per_call)
+                model.render_clip(p[a:b], sc.intrinsics, H, W, cond_feat=cf[a:b], bg_color=bg_color, bg_coords=bg_coords, pose6=p6[a:b] if p6 is not None else None,
+                                  T_thresh=sc.T_thresh, frames_per_call=args.frames_per_call, out=u8[a:b], as_uint8=True)
+                og.push(u8, a, b)
+            out = og.finish()
+        else:
+            out = model.render_clip(p, sc.intrinsics, H, W, cond_feat=cf, bg_color=bg_color, bg_coords=bg_coords, pose6=p6,
+                                    T_thresh=sc.T_thresh, frames_per_call=args.frames_per_call, out=u8, as_uint8=True)
         if rank == 0:
             u8_host.copy_(out, non_blocking=True)
 
@@ -443,7 +453,7 @@ def _main(args, out):
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "mlp_precision": args.precision, "frames_per_gpu_per_step": T, "frames_per_call": args.frames_per_call,
                            "S_valid_samples_per_frame": S_per_frame, "P_torso_pixels_per_frame": P_per_frame, "B_total": int(st[0, 0]),
-                           "parallelism": f"frame-sharded x{world}, 1 all-gather of uint8 RGB" if world > 1 else "single GPU",
+                           "parallelism": f"frame-sharded x{world}, uint8 RGB all-gathered chunk by chunk over NCCL, overlapped with the next chunk's kernels" if world > 1 else "single GPU",
                            "l2": "per-step working set (786 MB fp32 frames out + 1.8 GB workspace) >> 126 MB L2; grid tables (14.4 MB) are L2-resident by design"},
                 "clocks": clocks, "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                           "note": "pinned host poses+conditioning in (H2D, pose conversion and conditioning nets inside the timed "

@@ -47,6 +47,38 @@ def gather_frames(local: torch.Tensor, T: int, group=None) -> torch.Tensor:
     return torch.cat(pieces, 0) if any(p.shape[0] != blk for p in pieces) else full[: T]
 
 
+class OverlappedGather:
+    """All-gather of a clip in CHUNKS, overlapped with rendering: while the kernels of chunk k+1 run on the compute stream, the
+    uint8 frames of chunk k travel over NVLink on the collective's own stream (`async_op=True`).  Every rank renders the same
+    number of frames `t_local` (weak scaling; pad the clip otherwise).  Usage:
+
+        og = OverlappedGather(t_local, frame_shape, dtype, device)       # once; owns the [world, t_local, ...] result buffer
+        for a, b in chunks: render frames [a, b) into local[a:b]; og.push(local, a, b)
+        full = og.finish()                                               # [world * t_local, ...] in video order
+    """
+
+    def __init__(self, t_local, frame_shape, dtype, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.full = torch.empty((self.world, t_local) + tuple(frame_shape), dtype=dtype, device=device)
+        self.t_local = t_local
+        self.work = []
+
+    def push(self, local, a, b):
+        if self.world == 1:
+            self.full[0, a:b].copy_(local[a:b])
+            return
+        # the chunk must be complete before the collective reads it: NCCL's stream waits on the current (compute) stream
+        outs = [self.full[r, a:b] for r in range(self.world)]       # each a contiguous slab of the result
+        self.work.append(dist.all_gather(outs, local[a:b], group=self.group, async_op=True))
+
+    def finish(self):
+        for w in self.work:
+            w.wait()                                                 # makes the current stream wait for the collective
+        self.work = []
+        return self.full.view((self.world * self.t_local,) + tuple(self.full.shape[2:]))
+
+
 def to_uint8(rgb: torch.Tensor) -> torch.Tensor:
     """(x * 255).int() -> uint8, exactly what the driver writes to the video (genefacepp_infer.py:469, 505)."""
     return (rgb * 255.0).to(torch.int32).clamp_(0, 255).to(torch.uint8)

@@ -69,3 +69,32 @@ def test_sharded_render_and_gather_world2(T):
 def test_to_uint8_matches_the_driver_conversion():
     x = torch.tensor([0.0, 0.5, 0.999, 1.0])
     assert gdist.to_uint8(x).tolist() == [0, 127, 254, 255]      # (x * 255).int(), inference/genefacepp_infer.py:469
+
+
+def _worker_og(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    T = 6                                                    # frames per rank (weak scaling), chunks of 4 + 2
+    local = (torch.arange(T).view(T, 1, 1) + 10 * rank).expand(T, 5, 3).to(torch.uint8).contiguous()
+    og = gdist.OverlappedGather(T, (5, 3), torch.uint8, "cpu")
+    for a, b in ((0, 4), (4, 6)):
+        og.push(local, a, b)                                 # chunk-wise, asynchronous
+    full = og.finish()
+    q.put((rank, tuple(full.shape), full[:, 0, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_overlapped_chunked_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_og, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, shape, vals in res:
+        assert shape == (12, 5, 3)
+        assert vals == [0, 1, 2, 3, 4, 5, 10, 11, 12, 13, 14, 15], (rank, vals)   # rank-major = video order, on every rank
