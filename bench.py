@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--frames-per-call", type=int, default=50)
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the bounded CPU-baseline sample (~3.5 s each on the box)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-mode", action="store_true", help="skip measuring the other precision mode (fp16 <-> robust) beside the headline one")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own CUDA kernels (oracle/_ref) beside ours")
     ap.add_argument("--precision", default=os.environ.get("GFPP_BENCH_PRECISION", DEFAULT_PRECISION), choices=["fp32", "fp16", "bf16x3", "bf16", "robust"],
                     help="arithmetic of the head MLP GEMMs (marching/gather/compositing are fp32 in every mode)")
@@ -168,6 +169,64 @@ def cpu_reference_fps(args, n_frames, keep_images=False, rays=None):
     return n_frames / dt, cores, dt, S
 
 
+def measure_other_mode(args, sc, model, prec, poses_dev, pose6_dev, cond_dev, bg_color, bg_coords, rgb, hbm, S_per_frame, ref):
+    """The other tensor-core precision mode on the SAME workload in the same run (N = 1): one timed step of the device-resident clip,
+    its head-kernel roofline fraction, parity against the oracle frames of the cpu_baseline leg, and -- for both modes -- the max-abs
+    error on the 'lively' well-conditioned scene (MLP gain 4, table amplitude ~ 1/resolution, 64x64) where plain fp16 does not hold 1e-3."""
+    import ctypes
+    import torch
+    from genefaceplusplus_b200 import _capi, scene as scn
+    from genefaceplusplus_b200.renderer import RADNeRF, RADNeRFTorso
+    L = _capi.lib()
+    H = W = args.size
+    T = poses_dev.shape[0]
+    cls = RADNeRF if args.head_only else RADNeRFTorso
+    m = cls(sc.hparams); m.load_state_dict(sc.state, strict=True); m.density_scale = sc.density_scale; m.mlp_precision = prec
+    m = m.to(poses_dev.device).eval()
+    feat = m.cal_cond_feat_clip(cond_dev)[:T]
+    kw = dict(cond_feat=feat, bg_color=bg_color, bg_coords=bg_coords, pose6=pose6_dev, T_thresh=sc.T_thresh, frames_per_call=args.frames_per_call, out=rgb)
+    for _ in range(2):
+        m.render_clip(poses_dev, sc.intrinsics, H, W, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); m.render_clip(poses_dev, sc.intrinsics, H, W, **kw); e1.record(); torch.cuda.synchronize()
+    fps = T / (e0.elapsed_time(e1) / 1000.0)
+    L.gfpp_profile_enable(1)
+    Fc = min(args.frames_per_call, T)
+    m.render_clip(poses_dev[:Fc], sc.intrinsics, H, W, **{**kw, "cond_feat": feat[:Fc], "pose6": None if pose6_dev is None else pose6_dev[:Fc], "out": rgb[:Fc]})
+    buf = (ctypes.c_float * 4)(); _capi.check(L.gfpp_profile_read(buf), "profile_read")
+    L.gfpp_profile_enable(0)
+    head_t = buf[0] / 1000.0
+    out = {"precision": prec, "value": fps, "unit": "frames/s", "steps": 1,
+           "roofline_frac": Fc * (S_per_frame * 2048 + H * W * 20) / head_t / 1e9 / hbm, "head_launch_ms": buf[0]}
+    if ref is not None:
+        ref_img, ref_knife = ref
+        Fp = ref_img.shape[0]
+        mine = m.render_clip(poses_dev[:Fp], sc.intrinsics, H, W, **{**kw, "cond_feat": feat[:Fp], "pose6": None if pose6_dev is None else pose6_dev[:Fp], "out": None}).float().cpu()
+        d = (mine - ref_img).abs().max(-1).values
+        mse = ((mine.double() - ref_img.double()) ** 2).mean().item()
+        out["parity"] = {"max_abs": d[~(ref_knife < 1e-3)].max().item(), "n_over_1e-3": int((d > 1e-3).sum()),
+                         "psnr": 999.0 if mse == 0 else 10 * math.log10(1.0 / mse)}
+        # lively scene, both modes, 64x64 against the oracle
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import lively_state
+        from oracle.render import OracleModel
+        ls = scn.Scene(H=64, W=64, T=4, torso=False, density_scale=1.0, table_decay=1.0, table_amp=1.0)
+        st = lively_state(ls.state, 4.0)
+        fi = ls.frame_inputs(0)
+        orc = OracleModel(st, ls.hparams); orc.density_scale = ls.density_scale
+        r = orc.render(fi["rays_o"], fi["rays_d"], fi["cond"], fi["bg_coords"], fi["poses"], bg_color=fi["bg_color"], T_thresh=ls.T_thresh, **ls.hparams)
+        liv = {}
+        for p in ("fp16", "robust"):
+            lm = RADNeRF(ls.hparams); lm.load_state_dict(st, strict=True); lm.density_scale = ls.density_scale; lm.mlp_precision = p
+            lm = lm.to(poses_dev.device).eval()
+            o = lm.render(fi["rays_o"].cuda(), fi["rays_d"].cuda(), fi["cond"].cuda(), fi["bg_coords"].cuda(), fi["poses"].cuda(),
+                          bg_color=fi["bg_color"].cuda(), T_thresh=ls.T_thresh, **ls.hparams)
+            liv[p] = (o["rgb_map"].cpu().view(-1, 3) - r["rgb_map"].view(-1, 3)).abs().max().item()
+        out["lively_scene_max_abs"] = liv
+    return out
+
+
 def workload_name(args):
     return (f"May {'head-NeRF' if args.head_only else 'head+torso two-pass'} {args.size}x{args.size}, {args.frames}-frame driving clip per GPU, "
             f"max_steps=16, T_thresh=0.01, density_scale={args.density_scale:g}")
@@ -196,6 +255,15 @@ def run_reference(args, out=sys.stdout):
                                      "has no CPU implementation of its native ops and does not travel to this box); `cores` = calibrated thread count"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=out)
+
+
+_T0 = time.time()
+
+
+def _stage(msg):
+    """Progress marks on stderr (GFPP_BENCH_VERBOSE=1): where a multi-rank run is when it is slow or stuck."""
+    if os.environ.get("GFPP_BENCH_VERBOSE"):
+        print(f"[bench r{os.environ.get('RANK', '0')} +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
 def _claim_stdout():
@@ -258,8 +326,6 @@ def _main(args, out):
     u8_host = torch.empty(T * world if rank == 0 else 1, N, 3, dtype=torch.uint8).pin_memory()
     launches = 0
 
-    og = gdist.OverlappedGather(T, (N, 3), torch.uint8, dev) if world > 1 else None
-
     def step_device():
         nonlocal launches
         feat = model.cal_cond_feat_clip(cond_dev)[s:e]
@@ -275,11 +341,9 @@ def _main(args, out):
                                       **({"u8_out": u8[a:b]} if world > 1 else {"rgb_out": rgb[a:b]}))
             stats_acc.append(res["stats"])
             n0 += model.last_launch_count
-            if world > 1:
-                og.push(u8, a, b)          # this chunk's uint8 frames go out over NVLink while the next chunk renders
         launches += n0
         if world > 1:
-            return og.finish()
+            return gdist.gather_frames(u8, T * world)      # ONE all-gather of the uint8 clip (north_star)
         return rgb
 
     def step_e2e():
@@ -290,16 +354,10 @@ def _main(args, out):
         c = cond_host.to(dev, non_blocking=True)
         p6 = scn.convert_poses(poses_host).to(dev, non_blocking=True) if not args.head_only else None
         cf = model.cal_cond_feat_clip(c)[s:e]
+        out = model.render_clip(p, sc.intrinsics, H, W, cond_feat=cf, bg_color=bg_color, bg_coords=bg_coords, pose6=p6,
+                                T_thresh=sc.T_thresh, frames_per_call=args.frames_per_call, out=u8, as_uint8=True)
         if world > 1:
-            for a in range(0, T, args.frames_per_call):
-                b = min(T, a + args.frames_per_call)
-                model.render_clip(p[a:b], sc.intrinsics, H, W, cond_feat=cf[a:b], bg_color=bg_color, bg_coords=bg_coords, pose6=p6[a:b] if p6 is not None else None,
-                                  T_thresh=sc.T_thresh, frames_per_call=args.frames_per_call, out=u8[a:b], as_uint8=True)
-                og.push(u8, a, b)
-            out = og.finish()
-        else:
-            out = model.render_clip(p, sc.intrinsics, H, W, cond_feat=cf, bg_color=bg_color, bg_coords=bg_coords, pose6=p6,
-                                    T_thresh=sc.T_thresh, frames_per_call=args.frames_per_call, out=u8, as_uint8=True)
+            out = gdist.gather_frames(out, T * world)
         if rank == 0:
             u8_host.copy_(out, non_blocking=True)
 
@@ -312,9 +370,11 @@ def _main(args, out):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing ----------------
+    _stage("setup done, warm-up")
     for _ in range(max(args.warmup, 3)):
         step_device()
     sync_all()
+    _stage("warm-up done, timing")
     stats_acc.clear(); launches = 0
     sampler = ClockSampler(local)
     if rank == 0:
@@ -338,6 +398,7 @@ def _main(args, out):
     P_per_frame = st[:, 3].float().mean().item()
     fps = world * T * args.steps / (ms / 1000.0)
 
+    _stage("device-resident timing done")
     # ---------------- dominant-kernel roofline (live, CUDA events inside libgfpp) ----------------
     L.gfpp_profile_enable(1)
     head_ms, pass2_ms, epi_ms, pre_ms = [], [], [], []
@@ -389,6 +450,7 @@ def _main(args, out):
                 "tensor_note": "algorithmic MLP flops per second / measured sustained dense bf16 peak (MEASURED_PEAKS.json)"}
 
     # ---------------- end to end (host buffers in, uint8 frames out) ----------------
+    _stage("roofline leg done, end-to-end")
     for _ in range(2):
         step_e2e()
     sync_all()
@@ -402,6 +464,7 @@ def _main(args, out):
     if world > 1:
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e2e_fps = world * T * args.steps / (ems.item() / 1000.0)
+    _stage("end-to-end done")
     h2d = poses_host.numel() * 4 + cond_host.numel() * 4 + (0 if args.head_only else T * 6 * 4)
     d2h = u8_host.numel()
 
@@ -444,6 +507,10 @@ def _main(args, out):
         except Exception as ex:   # a baseline measurement must never take the bench down
             gpu_ref = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_mode and args.precision in ("fp16", "robust"):
+        other = measure_other_mode(args, sc, model, "robust" if args.precision == "fp16" else "fp16", poses_dev, pose6_dev, cond_dev, bg_color, bg_coords,
+                                   rgb, hbm, S_per_frame, (ref_img, ref_knife) if parity is not None else None)
     if rank == 0:
         line = {"metric": metric_name(args), "value": fps,
                 "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -453,13 +520,14 @@ def _main(args, out):
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "mlp_precision": args.precision, "frames_per_gpu_per_step": T, "frames_per_call": args.frames_per_call,
                            "S_valid_samples_per_frame": S_per_frame, "P_torso_pixels_per_frame": P_per_frame, "B_total": int(st[0, 0]),
-                           "parallelism": f"frame-sharded x{world}, uint8 RGB all-gathered chunk by chunk over NCCL, overlapped with the next chunk's kernels" if world > 1 else "single GPU",
+                           "parallelism": f"frame-sharded x{world}, one NCCL all-gather of the uint8 clip at the end" if world > 1 else "single GPU",
                            "l2": "per-step working set (786 MB fp32 frames out + 1.8 GB workspace) >> 126 MB L2; grid tables (14.4 MB) are L2-resident by design"},
                 "clocks": clocks, "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                           "note": "pinned host poses+conditioning in (H2D, pose conversion and conditioning nets inside the timed "
                                                   "region), uint8 [T,H,W,3] frames written by the epilogue kernel" +
                                                   (", all-gather of the uint8 clip, D2H of the whole clip on rank 0" if world > 1 else ", D2H of the clip")},
-                "gpu_launches": timed_launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "gpu_reference": gpu_ref}
+                "gpu_launches": timed_launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "gpu_reference": gpu_ref,
+                "other_mode": other}
         print(json.dumps(line), file=out)
     if world > 1:
         dist.destroy_process_group()

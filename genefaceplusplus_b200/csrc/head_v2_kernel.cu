@@ -575,9 +575,18 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
                 release(2);
             }
         };
-#define SLOT_BEGIN(sv)                            \
-    mbar_wait(&ms.a_ready[sv], apar);             \
-    fence_after_sync();                           \
+        // Slots of a layer are served in index order (blocking waits) or -- `relaxed` -- in the order their owners arrive: a sweep of
+        // non-blocking tests serves whoever is ready; only when nobody is does the warp block on the first slot still pending.
+        const bool relaxed = (t.flags & 1u) != 0u;
+#define FOR_SLOTS                                                                                                     \
+    for (uint32_t pend = (1u << NSLOT) - 1u, force = relaxed ? 0u : 1u, got = 0u; pend; force = (relaxed && got) ? 0u : 1u, got = 0u) \
+        _Pragma("unroll") for (int s = 0; s < NSLOT; ++s)
+#define SLOT_BEGIN(sv)                                                         \
+    if (!((pend >> (sv)) & 1u)) continue;                                      \
+    if (force) { mbar_wait(&ms.a_ready[sv], apar); if (relaxed) force = 0u; }  \
+    else if (!mbar_test(&ms.a_ready[sv], apar)) continue;                      \
+    pend &= ~(1u << (sv)); got = 1u;                                           \
+    fence_after_sync();                                                        \
     if (elect_one()) {
 #define SLOT_END(sv)                              \
         mma_commit(&ms.d_ready[sv]);              \
@@ -591,8 +600,7 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             } else {
                 const uint32_t w0 = tile(0), w1 = tile(1);
                 fence_after_sync();
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) {
+                FOR_SLOTS {
                     SLOT_BEGIN(s)
                     mma_sw(d_of(s), h_of(s, 0), w0, 4, idesc128, 0u);
                     mma_sw(d_of(s), h_of(s, 1), w1, 2, idesc128, 1u);
@@ -613,8 +621,7 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             } else {
                 const uint32_t w0 = tile(0), w1 = tile(1);
                 fence_after_sync();
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) {
+                FOR_SLOTS {
                     SLOT_BEGIN(s)
                     mma_sw(d_of(s), h_of(s, 0), w0, 4, idesc128, 0u);
                     mma_sw(d_of(s), h_of(s, 1), w1, 4, idesc128, 1u);
@@ -624,8 +631,7 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             }
             apar ^= 1u;
             // ---- ambient out: N = 16 group from the resident tiles, into columns 128..143 ----
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s) {
+            FOR_SLOTS {
                 SLOT_BEGIN(s)
                 if (ROBUST) {
                     mma_sw(d_of(s) + 128u, l_of(s, 0), res_u + V2_RES_AMBN_HI, 4, idesc16, 0u);
@@ -645,8 +651,7 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             {
                 const uint32_t w0 = tile(0);
                 fence_after_sync();
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) {
+                FOR_SLOTS {
                     SLOT_BEGIN(s)
                     mma_sw(d_of(s), h_of(s, 0), w0, 4, idesc128, 0u);
                     SLOT_END(s)
@@ -658,8 +663,7 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             {
                 const uint32_t w0 = tile(0), w1 = tile(1);
                 fence_after_sync();
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) {
+                FOR_SLOTS {
                     SLOT_BEGIN(s)
                     mma_sw(d_of(s), h_of(s, 0), w0, 4, idesc128, 0u);
                     mma_sw(d_of(s), h_of(s, 1), w1, 4, idesc128, 1u);
@@ -672,8 +676,7 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             {
                 const uint32_t w0 = tile(0), w1 = tile(1);
                 fence_after_sync();
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) {
+                FOR_SLOTS {
                     SLOT_BEGIN(s)
                     mma_sw(d_of(s), h_of(s, 0), w0, 4, idesc128, 0u);
                     mma_sw(d_of(s), h_of(s, 1), w1, 4, idesc128, 1u);
@@ -688,8 +691,7 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             {
                 const uint32_t w0 = tile(0), w1 = tile(1);
                 fence_after_sync();
-#pragma unroll
-                for (int s = 0; s < NSLOT; ++s) {
+                FOR_SLOTS {
                     SLOT_BEGIN(s)
                     mma_sw(d_of(s), h_of(s, 0), w0, 4, idesc128, 0u);
                     mma_sw(d_of(s), h_of(s, 1), w1, 4, idesc128, 1u);
@@ -700,8 +702,7 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
                 apar ^= 1u;
             }
             // ---- color out: N = 16 group ----
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s) {
+            FOR_SLOTS {
                 SLOT_BEGIN(s)
                 mma_sw(d_of(s) + 128u, h_of(s, 0), res_u + V2_RES_COLN, 4, idesc16, 0u);
                 mma_sw(d_of(s) + 128u, h_of(s, 1), res_u + V2_RES_COLN + 2048, 4, idesc16, 1u);
@@ -710,6 +711,7 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
             apar ^= 1u;
             if (!any) break;
         }
+#undef FOR_SLOTS
 #undef SLOT_BEGIN
 #undef SLOT_END
         // stop the loader: the NSTAGE tiles it has prefetched for a batch that never comes must land before the CTA may exit
@@ -755,7 +757,10 @@ cudaError_t launch_cond_images(const float *cond_feat, int n_frames, void *cond_
     return cudaGetLastError();
 }
 
-cudaError_t launch_head_v2(const HeadArgs &a, const HeadV2Args &t, int precision, cudaStream_t st) {
+cudaError_t launch_head_v2(const HeadArgs &a, const HeadV2Args &t_in, int precision, cudaStream_t st) {
+    HeadV2Args t = t_in;
+    // scheduling knob of the issue warp (bit 0: serve the slots of a layer in arrival order); GFPP_V2_RELAXED overrides the default for A/B runs
+    t.flags = getenv("GFPP_V2_RELAXED") ? (atoi(getenv("GFPP_V2_RELAXED")) ? 1u : 0u) : V2_DEFAULT_FLAGS;
     const bool robust = precision == FP16_ROBUST;
     if (!robust && precision != FP16_X1) return cudaErrorInvalidValue;
     const int blocks = sm_count();   // persistent: one CTA per SM (512 TMEM columns and ~200 KB of shared memory each)

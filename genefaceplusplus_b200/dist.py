@@ -49,10 +49,12 @@ def gather_frames(local: torch.Tensor, T: int, group=None) -> torch.Tensor:
 
 class OverlappedGather:
     """All-gather of a clip in CHUNKS, overlapped with rendering: while the kernels of chunk k+1 run on the compute stream, the
-    uint8 frames of chunk k travel over NVLink on the collective's own stream (`async_op=True`).  Every rank renders the same
-    number of frames `t_local` (weak scaling; pad the clip otherwise).  Usage:
+    uint8 frames of chunk k travel over NVLink on the collective's own stream (`all_gather_into_tensor(async_op=True)`, the same
+    collective `gather_frames` uses).  Every rank renders the same number of frames `t_local` (weak scaling; pad the clip
+    otherwise).  Each chunk lands in a staging slab [world, chunk, ...]; `finish()` waits for the collectives and moves the slabs
+    into video order (one device-side copy of the clip, ~1 ms for 1.5 GB).  Usage:
 
-        og = OverlappedGather(t_local, frame_shape, dtype, device)       # once; owns the [world, t_local, ...] result buffer
+        og = OverlappedGather(t_local, frame_shape, dtype, device)       # once; owns staging + result buffers
         for a, b in chunks: render frames [a, b) into local[a:b]; og.push(local, a, b)
         full = og.finish()                                               # [world * t_local, ...] in video order
     """
@@ -61,20 +63,24 @@ class OverlappedGather:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.full = torch.empty((self.world, t_local) + tuple(frame_shape), dtype=dtype, device=device)
+        self.stage = torch.empty((self.world * t_local,) + tuple(frame_shape), dtype=dtype, device=device) if self.world > 1 else None
         self.t_local = t_local
-        self.work = []
+        self.work = []          # (work handle, a, b)
 
     def push(self, local, a, b):
         if self.world == 1:
             self.full[0, a:b].copy_(local[a:b])
             return
-        # the chunk must be complete before the collective reads it: NCCL's stream waits on the current (compute) stream
-        outs = [self.full[r, a:b] for r in range(self.world)]       # each a contiguous slab of the result
-        self.work.append(dist.all_gather(outs, local[a:b], group=self.group, async_op=True))
+        # staging slab of this chunk: rows [world * a, world * b) viewed as [world, b - a, ...]; NCCL's stream waits on the current
+        # (compute) stream, so the chunk is complete before the collective reads it
+        slab = self.stage[self.world * a: self.world * b]
+        self.work.append((dist.all_gather_into_tensor(slab, local[a:b].contiguous(), group=self.group, async_op=True), a, b))
 
     def finish(self):
-        for w in self.work:
+        for w, a, b in self.work:
             w.wait()                                                 # makes the current stream wait for the collective
+            slab = self.stage[self.world * a: self.world * b].view((self.world, b - a) + tuple(self.full.shape[2:]))
+            self.full[:, a:b].copy_(slab)
         self.work = []
         return self.full.view((self.world * self.t_local,) + tuple(self.full.shape[2:]))
 
