@@ -46,7 +46,7 @@ constexpr uint32_t D_COLS = 144;     // TMEM columns per slot: 128 wide outputs 
 template <bool ROBUST>
 struct Cfg {
     static constexpr int NSLOT = ROBUST ? 2 : 3;
-    static constexpr int NSTAGE = ROBUST ? 3 : 4;
+    static constexpr int NSTAGE = 4;   // robust: 4 stages fit with 240 bytes to spare; with 3 the lo-image tiles of ambient L1 arrived late (7.4 K cycles of wait)
     static constexpr int NTILE = ROBUST ? V2_NTILE_ROBUST : V2_NTILE_X1;
     static constexpr int NWORK = 4 * NSLOT;                 // row-owner warps
     static constexpr int NT = 32 * (NWORK + 2);             // + issue warp + loader warp
@@ -294,6 +294,9 @@ __global__ void __launch_bounds__(Cfg<ROBUST>::NT, 1) k_head_v2(const __grid_con
                 }
                 __syncwarp();
             }
+            // the records the warp will adopt next (64 B each, read once, from L2 or DRAM): pull them towards L1 a batch ahead
+            if (a.pass == 1 && wf.next + lane < wf.end)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.hits + 4 * (size_t)(wf.next + lane)));
         };
         // eight levels [8 * half, 8 * half + 8) of the position grid at the NEXT sample -> feat / featl
         auto prefetch_pos = [&](int half) {
