@@ -36,11 +36,13 @@ using namespace gfpp;
 
 namespace {
 
+// per-thread state only (the library is thread-compatible: nothing below is shared between host threads)
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
-bool g_profile = false;
-unsigned long long *g_phase = nullptr;
-cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+thread_local bool g_profile = false;                 // opt-in diagnostics of the calling thread (bench.py, tools/phase_breakdown.py)
+thread_local unsigned long long *g_phase = nullptr;
+thread_local cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+thread_local int g_ev_dev = -1;                      // device the events were created on
 
 int fail(int code, const char *fmt, const char *detail = "") {
     snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -231,9 +233,14 @@ int gfpp_version(void) { return 100; }
 int gfpp_last_launch_count(void) { return g_launches; }
 
 int gfpp_profile_enable(int on) {
-    if (on && !g_ev[0]) {
-        for (int i = 0; i < 5; ++i)
+    int dev = -1;
+    if (on && cudaGetDevice(&dev) != cudaSuccess) return fail(GFPP_ERR_CUDA, "no CUDA device%s");
+    if (on && (!g_ev[0] || g_ev_dev != dev)) {   // events belong to a device: (re)create them for the current one
+        for (int i = 0; i < 5; ++i) {
+            if (g_ev[i]) cudaEventDestroy(g_ev[i]);
             if (cudaEventCreate(&g_ev[i]) != cudaSuccess) return fail(GFPP_ERR_CUDA, "cudaEventCreate failed%s");
+        }
+        g_ev_dev = dev;
     }
     g_profile = on != 0;
     return GFPP_OK;

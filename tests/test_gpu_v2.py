@@ -148,3 +148,23 @@ def test_one_process_two_devices():
                      bg_color=fi["bg_color"].to(dev), T_thresh=sc.T_thresh, **sc.hparams)
         outs.append(o["rgb_map"].cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_host_side_validation_and_repacking():
+    """Inputs the C entry point cannot check (it only sees pointers) are rejected on the host; in-place edits of the model's tables
+    trigger a repack (tensor._version is part of the pack key)."""
+    sc = scn.Scene(H=32, W=32, T=2, torso=True, density_scale=8.0)
+    m = build_model(sc, precision="fp16")
+    poses = torch.stack([sc.pose(t) for t in range(2)])
+    kw = dict(cond_seq=sc.cond, bg_coords=sc.bg_coords, T_thresh=sc.T_thresh)
+    a = m.render_clip(poses, sc.intrinsics, 32, 32, bg_color=sc.bg_color, **kw)
+    with pytest.raises(ValueError):
+        m.render_clip(poses, sc.intrinsics, 32, 32, bg_color=torch.rand(17, 3), **kw)              # neither 1 nor N rows
+    with pytest.raises(ValueError):
+        m.render_clip(poses, sc.intrinsics, 32, 32, bg_color=sc.bg_color, out=torch.empty(2, 32 * 32, 3, device="cuda"), as_uint8=True, **kw)   # fp32 buffer for uint8 frames
+    with pytest.raises(ValueError):
+        m.render_frames(m.cal_cond_feat_clip(sc.cond.cuda())[:2], rays_o=torch.zeros(2, 50, 3), rays_d=torch.zeros(2, 49, 3))
+    with torch.no_grad():
+        m.position_embedder.embeddings.mul_(0.5)                                                       # in place: no invalidate() call
+    b = m.render_clip(poses, sc.intrinsics, 32, 32, bg_color=sc.bg_color, **kw)
+    assert (a - b).abs().max().item() > 1e-4, "the packed (sector-packed, fp16) copy of the table must have been rebuilt"
