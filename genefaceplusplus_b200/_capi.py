@@ -54,6 +54,15 @@ class Frames(ctypes.Structure):
                 ("T_thresh", c_f)]
 
 
+class SrDesc(ctypes.Structure):
+    _fields_ = [("conv_in_w", c_void_p), ("conv0_w", c_void_p), ("up_w", c_void_p), ("conv1_w", c_void_p),
+                ("bias", c_void_p * 4), ("rgb_w", c_void_p * 2), ("rgb_b", c_void_p * 2)]
+
+
+class SrModel(ctypes.Structure):
+    _fields_ = [("opaque", ctypes.c_uint64 * 32)]
+
+
 class Outputs(ctypes.Structure):
     _fields_ = [("rgb_map", c_void_p), ("depth_map", c_void_p), ("weights_sum", c_void_p),
                 ("torso_alpha_map", c_void_p), ("torso_rgb_map", c_void_p), ("torso_deform", c_void_p),
@@ -65,6 +74,7 @@ EXPORTS = [
     "gfpp_composite_rays", "gfpp_grid_encode_forward", "gfpp_sh_encode_forward", "gfpp_freq_encode_forward",
     "gfpp_model_packed_bytes", "gfpp_model_pack", "gfpp_render_workspace_bytes", "gfpp_render_frames",
     "gfpp_last_launch_count", "gfpp_profile_enable", "gfpp_profile_read", "gfpp_profile_phases", "gfpp_tc_selftest", "gfpp_debug_generate_rays",
+    "gfpp_sr_packed_bytes", "gfpp_sr_pack", "gfpp_sr_workspace_bytes", "gfpp_sr_forward",
 ]
 
 
@@ -96,6 +106,13 @@ def lib():
         L.gfpp_profile_phases.argtypes = [c_void_p]
         L.gfpp_debug_generate_rays.argtypes = [c_void_p, c_u32, c_f, c_f, c_f, c_f, c_u32, c_u32, c_void_p, c_void_p, c_void_p]
         L.gfpp_tc_selftest.argtypes = [c_void_p, c_void_p, c_u32, c_u32, c_int, c_int, c_void_p, c_void_p, c_void_p]
+        L.gfpp_sr_packed_bytes.restype = c_size_t
+        L.gfpp_sr_packed_bytes.argtypes = []
+        L.gfpp_sr_pack.argtypes = [ctypes.POINTER(SrDesc), c_void_p, c_size_t, ctypes.POINTER(SrModel), c_void_p]
+        L.gfpp_sr_workspace_bytes.restype = c_size_t
+        L.gfpp_sr_workspace_bytes.argtypes = [c_u32, c_u32]
+        L.gfpp_sr_forward.argtypes = [ctypes.POINTER(SrModel), c_u32, c_u32, c_void_p, ctypes.POINTER(c_void_p * 4), c_u32, c_void_p,
+                                      c_int, c_void_p, c_size_t, c_void_p]
         _lib = L
     return _lib
 

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "head_kernel.cuh"
 #include "launch.cuh"
+#include "sr_kernel.cuh"
 #include "torso_kernel.cuh"
 
 namespace gfpp {
@@ -692,6 +693,132 @@ int gfpp_render_frames(const gfpp_model *model, const gfpp_frames *fr, const gfp
                                                              a.n_frames, out->stats);
         CK(cudaGetLastError());
     }
+    return GFPP_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ (C) super-resolution head (sr_kernel.cu)
+namespace {
+struct SrHost {
+    uint32_t magic;
+    const float *conv_in_w, *bias[4], *rgb_w[2], *rgb_b[2];
+    const unsigned char *tiles[3];
+};
+static_assert(sizeof(SrHost) <= sizeof(gfpp_sr_model), "gfpp_sr_model opaque storage too small");
+constexpr uint32_t kSrMagic = 0x67667372u;  // "gfsr"
+struct SrPacked { size_t conv_in_w, bias[4], rgb_w[2], rgb_b[2], tiles[3], total; };
+SrPacked sr_packed_layout() {
+    SrPacked L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
+    L.conv_in_w = take(27 * 128 * 4);
+    const int nb[4] = {128, 128, 64, 64};
+    for (int i = 0; i < 4; ++i) L.bias[i] = take((size_t)nb[i] * 4);
+    L.rgb_w[0] = take(3 * 128 * 4); L.rgb_w[1] = take(3 * 64 * 4);
+    L.rgb_b[0] = take(16); L.rgb_b[1] = take(16);
+    for (int l = 0; l < 3; ++l) L.tiles[l] = take((size_t)sr_layer_weight_bytes(l));
+    L.total = o;
+    return L;
+}
+struct SrWork { size_t x0a, x0b, img0, x1a, total; };
+SrWork sr_work_layout(uint32_t F, uint32_t R) {
+    SrWork W;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
+    const size_t px = (size_t)F * R * R;
+    W.x0a = take(px * 128 * 2);
+    W.x0b = take(px * 128 * 2);
+    W.img0 = take(px * 3 * 4);
+    W.x1a = take(px * 4 * 64 * 2);
+    W.total = o;
+    return W;
+}
+}  // namespace
+
+extern "C" {
+
+size_t gfpp_sr_packed_bytes(void) { return sr_packed_layout().total; }
+
+int gfpp_sr_pack(const gfpp_sr_desc *d, void *packed, size_t packed_bytes, gfpp_sr_model *model, void *stream) {
+    if (!d || !packed || !model) return fail(GFPP_ERR_INVALID, "sr_pack: null pointer%s");
+    if (!d->conv_in_w || !d->conv0_w || !d->up_w || !d->conv1_w) return fail(GFPP_ERR_INVALID, "sr_pack: null weight%s");
+    for (int i = 0; i < 4; ++i) if (!d->bias[i]) return fail(GFPP_ERR_INVALID, "sr_pack: null bias%s");
+    for (int i = 0; i < 2; ++i) if (!d->rgb_w[i] || !d->rgb_b[i]) return fail(GFPP_ERR_INVALID, "sr_pack: null toRGB weight%s");
+    const SrPacked L = sr_packed_layout();
+    if (packed_bytes < L.total) return fail(GFPP_ERR_WORKSPACE, "sr_pack: packed buffer too small%s");
+    if (((uintptr_t)packed & 1023u) != 0) return fail(GFPP_ERR_INVALID, "sr_pack: packed buffer must be 1024-byte aligned%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *base = (char *)packed;
+    g_launches = 0;
+    CKN(cudaMemsetAsync(packed, 0, L.total, st));
+    CKN(cudaMemcpyAsync(base + L.conv_in_w, d->conv_in_w, 27 * 128 * 4, cudaMemcpyDeviceToDevice, st));
+    const int nb[4] = {128, 128, 64, 64};
+    for (int i = 0; i < 4; ++i) CKN(cudaMemcpyAsync(base + L.bias[i], d->bias[i], (size_t)nb[i] * 4, cudaMemcpyDeviceToDevice, st));
+    CKN(cudaMemcpyAsync(base + L.rgb_w[0], d->rgb_w[0], 3 * 128 * 4, cudaMemcpyDeviceToDevice, st));
+    CKN(cudaMemcpyAsync(base + L.rgb_w[1], d->rgb_w[1], 3 * 64 * 4, cudaMemcpyDeviceToDevice, st));
+    CKN(cudaMemcpyAsync(base + L.rgb_b[0], d->rgb_b[0], 12, cudaMemcpyDeviceToDevice, st));
+    CKN(cudaMemcpyAsync(base + L.rgb_b[1], d->rgb_b[1], 12, cudaMemcpyDeviceToDevice, st));
+    // GEMM matrices [N_total][9 * C_in] -> fp16 UMMA K-major SW128 tiles in the kernels' streaming order:
+    // chunk c covers k in [64c, 64c + 64) (tap c / CB, channel block c % CB); inside a chunk one tile per N-block
+    const float *mat[3] = {d->conv0_w, d->up_w, d->conv1_w};
+    for (int l = 0; l < 3; ++l) {
+        const int ld = 9 * sr_layer_cin(l), nrows = sr_layer_nrows(l);
+        unsigned char *dst = (unsigned char *)(base + L.tiles[l]);
+        for (int c = 0; c < sr_layer_nchunk(l); ++c)
+            for (int b = 0; b < sr_layer_nb(l); ++b)
+                CK(launch_pack_tc_tile(mat[l], ld, b * nrows, c * 64, nrows, 64, 0, 0, 0,
+                                       dst + ((size_t)c * sr_layer_nb(l) + b) * nrows * 128, nullptr, st));
+    }
+    SrHost m;
+    memset(&m, 0, sizeof(m));
+    m.magic = kSrMagic;
+    m.conv_in_w = (const float *)(base + L.conv_in_w);
+    for (int i = 0; i < 4; ++i) m.bias[i] = (const float *)(base + L.bias[i]);
+    for (int i = 0; i < 2; ++i) { m.rgb_w[i] = (const float *)(base + L.rgb_w[i]); m.rgb_b[i] = (const float *)(base + L.rgb_b[i]); }
+    for (int l = 0; l < 3; ++l) m.tiles[l] = (const unsigned char *)(base + L.tiles[l]);
+    memset(model, 0, sizeof(*model));
+    memcpy(model, &m, sizeof(m));
+    return GFPP_OK;
+}
+
+size_t gfpp_sr_workspace_bytes(uint32_t n_frames, uint32_t in_res) { return sr_work_layout(n_frames, in_res).total; }
+
+int gfpp_sr_forward(const gfpp_sr_model *model, uint32_t n_frames, uint32_t in_res, const float *rgb_in, const float *const noise[4],
+                    uint32_t noise_per_frame, float *out, int clamp01, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!model || !rgb_in || !out || !workspace) return fail(GFPP_ERR_INVALID, "sr_forward: null pointer%s");
+    SrHost m;
+    memcpy(&m, model, sizeof(m));
+    if (m.magic != kSrMagic) return fail(GFPP_ERR_INVALID, "sr_forward: model handle not initialised by gfpp_sr_pack%s");
+    if (n_frames == 0 || in_res == 0 || in_res % 128 != 0 || in_res > 1024) return fail(GFPP_ERR_UNSUPPORTED, "sr_forward: in_res must be a multiple of 128 (256 in the reference)%s");
+    if ((uint64_t)n_frames * in_res * in_res * 4 >= (1ull << 31)) return fail(GFPP_ERR_UNSUPPORTED, "sr_forward: too many frames per call%s");
+    const SrWork W = sr_work_layout(n_frames, in_res);
+    if (workspace_bytes < W.total) return fail(GFPP_ERR_WORKSPACE, "sr_forward: workspace too small%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    const int F = (int)n_frames, R = (int)in_res;
+    const long long lo = noise_per_frame ? (long long)R * R : 0, hi = noise_per_frame ? 4ll * R * R : 0;
+    g_launches = 0;
+    SrConvInArgs ci;
+    memset(&ci, 0, sizeof(ci));
+    ci.in = rgb_in; ci.F = F; ci.H = R; ci.W = R; ci.w = m.conv_in_w; ci.bias = m.bias[0];
+    ci.noise = noise ? noise[0] : nullptr; ci.noise_fstride = lo; ci.out = (__half *)(ws + W.x0a);
+    CK(launch_sr_conv_in(ci, st));
+    SrConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = (const __half *)(ws + W.x0a); a.F = F; a.H = R; a.W = R; a.wt = m.tiles[0]; a.bias = m.bias[1];
+    a.noise = noise ? noise[1] : nullptr; a.noise_fstride = lo; a.out = (__half *)(ws + W.x0b);
+    a.rgb_w = m.rgb_w[0]; a.rgb_b = m.rgb_b[0]; a.img_in = rgb_in; a.img_out = (float *)(ws + W.img0);
+    CK(launch_sr_conv(0, a, st));
+    memset(&a, 0, sizeof(a));
+    a.in = (const __half *)(ws + W.x0b); a.F = F; a.H = R; a.W = R; a.wt = m.tiles[1]; a.bias = m.bias[2];
+    a.noise = noise ? noise[2] : nullptr; a.noise_fstride = hi; a.out = (__half *)(ws + W.x1a);
+    CK(launch_sr_conv(1, a, st));
+    memset(&a, 0, sizeof(a));
+    a.in = (const __half *)(ws + W.x1a); a.F = F; a.H = 2 * R; a.W = 2 * R; a.wt = m.tiles[2]; a.bias = m.bias[3];
+    a.noise = noise ? noise[3] : nullptr; a.noise_fstride = hi;
+    a.rgb_w = m.rgb_w[1]; a.rgb_b = m.rgb_b[1]; a.img_in = (const float *)(ws + W.img0); a.img_out = out; a.clamp01 = clamp01;
+    CK(launch_sr_conv(2, a, st));
     return GFPP_OK;
 }
 

@@ -526,7 +526,7 @@ class RADNeRFwithSR(RADNeRF):
         return results
 
     @torch.no_grad()
-    def render_clip(self, poses_c2w, intrinsics, H=256, W=256, *args, sr_noise_mode="random", sr_frames_per_call=16, **kwargs):
+    def render_clip(self, poses_c2w, intrinsics, H=256, W=256, *args, sr_noise_mode="random", sr_frames_per_call=8, **kwargs):
         """Clip API: NeRF at 256x256 for all frames (libgfpp), then the SR head over chunks of frames.
         Returns the clamped 512x512 frames [T,3,512,512]; `intrinsics` are those of the 256x256 camera."""
         R = self.sr_input_resolution
@@ -538,9 +538,13 @@ class RADNeRFwithSR(RADNeRF):
         T = rgb.shape[0]
         out = torch.empty(T, 3, 2 * R, 2 * R, device=rgb.device, dtype=torch.float32)
         with torch.autocast(rgb.device.type, enabled=False):
-            for s in range(0, T, sr_frames_per_call):
-                e = min(T, s + sr_frames_per_call)
-                out[s:e] = self.sr_net(rgb[s:e].view(e - s, R, R, 3).permute(0, 3, 1, 2), noise_mode=sr_noise_mode).clamp(0, 1)
+            if self.sr_net.backend == "native":
+                # libgfpp's SR kernels read the renderer's [T,N,3] frames as they are and clamp in their last epilogue
+                self.sr_net.forward_native(rgb, noise_mode=sr_noise_mode, clamp=True, out=out, frames_per_call=sr_frames_per_call)
+            else:
+                for s in range(0, T, sr_frames_per_call):
+                    e = min(T, s + sr_frames_per_call)
+                    out[s:e] = self.sr_net(rgb[s:e].view(e - s, R, R, 3).permute(0, 3, 1, 2), noise_mode=sr_noise_mode).clamp(0, 1)
         return (out, stats) if want_stats else out
 
 

@@ -17,9 +17,18 @@ the reference's code:
     [1,3,3,1]^2 / 64 with gain 4 on the (2H+1)-sized result padded by one pixel -- the polyphase identity the reference's
     conv2d_resample uses (torch_utils/ops/conv2d_resample.py:118-133).
 
-Arithmetic is fp32 on every device (the reference switches these blocks to fp16 on CUDA; fp32 is the oracle's precision).
-This is host-side PyTorch (library convolutions): plumbing around the NeRF hot path, not a hand-written kernel yet.
+Two implementations live behind `Superresolution.forward`:
+
+  * CUDA tensors, `backend == "native"` (the default): libgfpp's hand-written sm_100a kernels (csrc/sr_kernel.cu through
+    gfpp_sr_pack / gfpp_sr_forward): one fp32 FFMA kernel for the 3-channel input layer and three implicit-GEMM tcgen05
+    kernels with fused noise / bias / leaky-ReLU / clamp / toRGB / skip epilogues; fp16 operands with fp32 accumulation
+    (the reference switches these blocks to fp16 on CUDA), toRGB and the skip path fp32.  `folded_weights()` is the host
+    half of that path: it folds modulation, demodulation and -- for the up-sampling layer -- the transposed stride-2
+    convolution together with its FIR filter into plain GEMM matrices.  A missing libgfpp raises (no silent eager path).
+  * `backend == "torch"` or CPU tensors: the plain fp32 convolutions below -- the math the goldens pin
+    (tests/golden/sr_head.npz) and the checker of the native path (tests/test_gpu_sr_native.py).
 """
+import ctypes
 import math
 
 import torch
@@ -138,6 +147,8 @@ class _Block(nn.Module):
 class Superresolution(nn.Module):
     """radnerf_sr.py:15-48.  forward(rgb [B,3,h,w] in [0,1]) -> [B,3,512,512] (not clamped; the caller clamps)."""
 
+    backend = "torch"    # FLIP-AFTER-GPU-VALIDATION -> "native".  CUDA tensors: libgfpp's sm_100a kernels; "torch": the fp32 convolutions below (always on CPU tensors)
+
     def __init__(self, channels=3, img_resolution=512, sr_antialias=True):
         super().__init__()
         if img_resolution != 512:
@@ -149,7 +160,151 @@ class Superresolution(nn.Module):
         self.block1 = _Block(128, 64, self.w_dim, 512, up=2)
         self.register_buffer("resample_filter", _binomial_filter())
 
+    # ------------------------------------------------------------------ host half of the native path
+    @torch.no_grad()
+    def folded_weights(self):
+        """The six layers as plain convolutions / GEMM matrices (fp32, on the parameters' device), given the constant
+        latent w = 1 (radnerf_sr.py:33-34); layouts as gfpp_sr_desc (include/gfpp.h) wants them:
+
+          conv_in_w [27,128]    block0.conv0, k = (ky*3+kx)*3 + ci                      (cross-correlation taps, padding 1)
+          conv0_w   [128,1152]  block0.conv1, k = (ky*3+kx)*128 + ci
+          up_w      [256,1152]  block1.conv0: y = FIR(conv_transpose2d(x, k, stride 2)) merged into four 3x3 kernels on the
+                                input grid, one per output phase (py, px): row (py*2+px)*64 + co produces pixel
+                                (2i+py, 2j+px).  With f = [1,3,3,1]/8 * 2 per axis (gain 4 in 2-D), u[U] = sum_a k[a] x[(U-a)/2]
+                                and y[Y] = sum_t f[t] u[Y+t-1]:  K_p[o] = sum_{t,a : t-1-a = 2o-p} f[t] k[a],  o in {-1,0,1};
+                                zero-extending x reproduces the padding of the reference's conv2d_resample exactly.
+          conv1_w   [64,576]    block1.conv1, k = (ky*3+kx)*64 + ci
+          bias[4], rgb_w[2] ([3,C]: toRGB weight * style / sqrt(C)), rgb_b[2]
+        """
+        dev = self.block0.conv0.weight.device
+        w = torch.ones(self.w_dim, dtype=torch.float32, device=dev)
+        b0, b1 = self.block0, self.block1
+        k00, k01 = b0.conv0.modulated_weight(w).float(), b0.conv1.modulated_weight(w).float()
+        k10, k11 = b1.conv0.modulated_weight(w).double(), b1.conv1.modulated_weight(w).float()
+        f1 = b1.conv0.resample_filter.double().sum(dim=0)        # separable: rows of outer(f,f)/64 sum to f/8
+        f1 = f1 / f1.sum() * 2.0                                 # [1,3,3,1]/8 * 2
+        O, I = k10.shape[:2]
+        K = torch.zeros(2, 2, O, I, 3, 3, dtype=torch.float64, device=dev)
+        for p in range(2):
+            for ty in range(4):
+                for ay in range(3):
+                    if (p + ty - 1 - ay) % 2:
+                        continue
+                    oy = (p + ty - 1 - ay) // 2 + 1
+                    for q in range(2):
+                        for tx in range(4):
+                            for ax in range(3):
+                                if (q + tx - 1 - ax) % 2:
+                                    continue
+                                ox = (q + tx - 1 - ax) // 2 + 1
+                                K[p, q, :, :, oy, ox] += f1[ty] * f1[tx] * k10[:, :, ay, ax]
+
+        def rgb(t):
+            s = t.affine(w) * t.weight_gain
+            return (t.weight[:, :, 0, 0] * s.view(1, -1)).float().contiguous(), t.bias.detach().float().contiguous()
+
+        r0w, r0b = rgb(b0.torgb)
+        r1w, r1b = rgb(b1.torgb)
+        return {
+            "conv_in_w": k00.permute(2, 3, 1, 0).reshape(27, 128).contiguous(),
+            "conv0_w": k01.permute(0, 2, 3, 1).reshape(128, 9 * 128).contiguous(),
+            "up_w": K.permute(0, 1, 2, 4, 5, 3).reshape(4 * O, 9 * I).float().contiguous(),
+            "conv1_w": k11.permute(0, 2, 3, 1).reshape(64, 9 * 64).contiguous(),
+            "bias": [b0.conv0.bias.detach().float().contiguous(), b0.conv1.bias.detach().float().contiguous(),
+                     b1.conv0.bias.detach().float().contiguous(), b1.conv1.bias.detach().float().contiguous()],
+            "rgb_w": [r0w, r1w], "rgb_b": [r0b, r1b],
+        }
+
+    def _layers(self):
+        return (self.block0.conv0, self.block0.conv1, self.block1.conv0, self.block1.conv1)
+
+    def _native_state(self):
+        """Packed weights of the native path, rebuilt when a parameter changes (in place or by load_state_dict)."""
+        from . import _capi
+        key = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        st = self.__dict__.get("_native")
+        if st is None or st["key"] != key:
+            dev = self.block0.conv0.weight.device
+            L = _capi.lib()
+            fw = self.folded_weights()
+            d = _capi.SrDesc()
+            keep = []
+            for name in ("conv_in_w", "conv0_w", "up_w", "conv1_w"):
+                setattr(d, name, _capi.ptr(fw[name], torch.float32))
+            for i in range(4):
+                d.bias[i] = _capi.ptr(fw["bias"][i], torch.float32)
+            for i in range(2):
+                d.rgb_w[i] = _capi.ptr(fw["rgb_w"][i], torch.float32)
+                d.rgb_b[i] = _capi.ptr(fw["rgb_b"][i], torch.float32)
+            packed = torch.empty(L.gfpp_sr_packed_bytes() + 1024, dtype=torch.uint8, device=dev)
+            off = (-packed.data_ptr()) % 1024
+            model = _capi.SrModel()
+            with torch.cuda.device(dev):
+                _capi.check(L.gfpp_sr_pack(ctypes.byref(d), _capi.c_void_p(packed.data_ptr() + off), packed.numel() - off,
+                                           ctypes.byref(model), _capi.stream_ptr(dev)), "gfpp_sr_pack")
+            strengths = [float(l.noise_strength) for l in self._layers()]       # one sync per (re)pack
+            st = {"key": key, "packed": packed, "model": model, "fw": fw, "strengths": strengths, "ws": None}
+            self.__dict__["_native"] = st
+        return st
+
+    @torch.no_grad()
+    def forward_native(self, rgb_flat, noise_mode="random", clamp=False, out=None, frames_per_call=8, noise_planes=None):
+        """rgb_flat [F, R*R, 3] fp32 CUDA in [0,1] (the layout the renderer writes `rgb_map` in), R = 256 -> [F,3,2R,2R]
+        through libgfpp's sm_100a kernels (4 launches per chunk of frames).  `noise_planes`: optional list of four tensors
+        ([res,res] shared by all frames or [F,res,res]; None entries = no noise), already multiplied by the layers'
+        noise_strength, instead of drawing them here (tests; callers that want reproducible 'random' noise)."""
+        from . import _capi
+        R = self.input_resolution
+        if not rgb_flat.is_cuda:
+            raise _capi.GfppError("the native SR head needs CUDA tensors (libgfpp has no CPU path)")
+        x = rgb_flat.reshape(-1, R * R, 3)
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        dev = x.device
+        F_ = x.shape[0]
+        st = self._native_state()
+        L = _capi.lib()
+        res = out if out is not None else torch.empty(F_, 3, 2 * R, 2 * R, device=dev, dtype=torch.float32)
+        if res.shape != (F_, 3, 2 * R, 2 * R) or res.dtype != torch.float32 or not res.is_contiguous():
+            raise ValueError(f"out must be a contiguous float32 [{F_},3,{2 * R},{2 * R}] tensor")
+        if noise_mode not in ("random", "const", "none"):
+            raise ValueError(f"noise_mode must be random / const / none, not {noise_mode!r}")
+        layers = self._layers()
+        for s0 in range(0, F_, frames_per_call):
+            n = min(frames_per_call, F_ - s0)
+            planes, arr = [], (_capi.c_void_p * 4)()
+            per_frame = noise_mode == "random"
+            if noise_planes is not None:
+                per_frame = any(p is not None and p.dim() == 3 for p in noise_planes)
+            for i, lay in enumerate(layers):
+                p = None
+                if noise_planes is not None:
+                    p = noise_planes[i]
+                    if p is not None:
+                        p = p.to(dev, torch.float32)
+                        p = (p[s0:s0 + n] if p.dim() == 3 else (p.expand(n, -1, -1) if per_frame else p)).contiguous()
+                        if p.shape[-2:] != (lay.resolution, lay.resolution):
+                            raise ValueError(f"noise plane {i} must be {lay.resolution}x{lay.resolution}")
+                elif noise_mode != "none" and st["strengths"][i] != 0.0:
+                    if noise_mode == "const":
+                        p = (lay.noise_const * lay.noise_strength).float().contiguous()
+                    else:
+                        p = (torch.randn(n, lay.resolution, lay.resolution, device=dev) * lay.noise_strength).float().contiguous()
+                planes.append(p)
+                arr[i] = _capi.ptr(p, torch.float32) if p is not None else None
+            need = L.gfpp_sr_workspace_bytes(n, R)
+            if st["ws"] is None or st["ws"].numel() < need or st["ws"].device != dev:
+                st["ws"] = torch.empty(need, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _capi.check(L.gfpp_sr_forward(ctypes.byref(st["model"]), n, R, _capi.ptr(x[s0:s0 + n], torch.float32), ctypes.byref(arr),
+                                              1 if per_frame else 0, _capi.ptr(res[s0:s0 + n], torch.float32),
+                                              1 if clamp else 0, _capi.ptr(st["ws"]), st["ws"].numel(), _capi.stream_ptr(dev)),
+                            "gfpp_sr_forward")
+        return res
+
     def forward(self, rgb, noise_mode="random"):
+        if rgb.is_cuda and self.backend == "native" and rgb.shape[-2:] == (self.input_resolution, self.input_resolution):
+            return self.forward_native(rgb.float().permute(0, 2, 3, 1).reshape(rgb.shape[0], -1, 3), noise_mode=noise_mode)
         x = rgb.float()
         if x.shape[-1] < self.input_resolution:
             x = F.interpolate(x, size=(self.input_resolution, self.input_resolution), mode="bilinear", align_corners=False,

@@ -24,6 +24,9 @@
  *      NeRFRenderer.render / RADNeRFTorso.render (modules/radnerfs/renderer.py:340-399,
  *      modules/radnerfs/radnerf_torso.py:129-197) for one or many frames per call:
  *        gfpp_model_packed_bytes / gfpp_model_pack / gfpp_render_workspace_bytes / gfpp_render_frames
+ *
+ *  (C) the SR checkpoints' extra stages: gfpp_sr_* (256 -> 512 super-resolution head) and
+ *      gfpp_torso_sr_* (the torso field of radnerf_torso_sr.py), declared at the end of this file.
  */
 #ifndef GFPP_H_
 #define GFPP_H_
@@ -210,6 +213,50 @@ GFPP_API int gfpp_debug_generate_rays(const float *poses_c2w, uint32_t n_frames,
                                       uint32_t img_h, uint32_t img_w, float *rays_o, float *rays_d, void *stream);
 /* number of kernels the last gfpp_render_frames call on this thread launched */
 GFPP_API int gfpp_last_launch_count(void);
+
+/* ------------------------------------------------------------------ (C) super-resolution head of the SR checkpoints
+ *
+ * Replaces `Superresolution.forward` (modules/radnerfs/radnerf_sr.py:15-48; StyleGAN2 blocks of
+ * modules/eg3ds/models/superresolution.py:159-257 and networks_stylegan2.py:286-475) for the 256 -> 512 head the
+ * `with_sr` checkpoints carry (inference/genefacepp_infer.py:464-465,480-481 takes `sr_rgb_map`).  The network is
+ * always run with the constant latent w = 1 (radnerf_sr.py:33-34), so the style modulation, the demodulation and the
+ * [1,3,3,1] resampling filter are constants of the checkpoint: the caller folds them into plain GEMM matrices (fp32,
+ * device) once -- genefaceplusplus_b200/superres.py::folded_weights documents the algebra -- and hands them over here:
+ *   conv_in_w  block0.conv0  [27][128]     k-major, k = (ky*3+kx)*3 + ci
+ *   conv0_w    block0.conv1  [128][1152]   k = (ky*3+kx)*128 + ci
+ *   up_w       block1.conv0  [256][1152]   transposed stride-2 conv + FIR merged into four 3x3 phase kernels on the input
+ *                                          grid, row = (py*2+px)*64 + co for output pixel (2y+py, 2x+px)
+ *   conv1_w    block1.conv1  [64][576]     k = (ky*3+kx)*64 + ci
+ *   bias[4]    conv biases (128, 128, 64, 64);  rgb_w[2] effective toRGB weights [3][128], [3][64];  rgb_b[2] [3]
+ * Operands of the three tensor-core layers are rounded to fp16 (fp32 accumulation), as the reference's use_fp16 blocks do. */
+typedef struct {
+    const float *conv_in_w;
+    const float *conv0_w;
+    const float *up_w;
+    const float *conv1_w;
+    const float *bias[4];
+    const float *rgb_w[2];
+    const float *rgb_b[2];
+} gfpp_sr_desc;
+
+typedef struct gfpp_sr_model {
+    uint64_t opaque[32];
+} gfpp_sr_model;
+
+GFPP_API size_t gfpp_sr_packed_bytes(void);
+/* Repack on `stream` into `packed` (device, 1024-byte aligned, >= gfpp_sr_packed_bytes); the desc's tensors are copied and
+ * may be freed once the stream has passed this call. */
+GFPP_API int gfpp_sr_pack(const gfpp_sr_desc *desc, void *packed, size_t packed_bytes, gfpp_sr_model *model, void *stream);
+GFPP_API size_t gfpp_sr_workspace_bytes(uint32_t n_frames, uint32_t in_res);
+/* rgb_in [F, in_res*in_res, 3] fp32 in [0,1] (the layout gfpp_render_frames writes `rgb_map` in) -> out [F, 3, 2*in_res,
+ * 2*in_res] fp32 (planar, as the reference returns it); clamp01 != 0 clamps it to [0,1] (every caller of the SR head does
+ * that next: radnerf_sr.py:208).  noise[i]: per-layer noise planes ALREADY multiplied by the layer's noise_strength
+ * (layers 0,1: in_res^2; layers 2,3: (2*in_res)^2), one plane shared by all frames (noise_mode 'const') or, with
+ * noise_per_frame != 0, F consecutive planes ('random'); NULL entries / a NULL array mean no noise ('none').
+ * in_res must be a multiple of 128 (256 in the reference).  Four kernel launches, no host sync, no allocation. */
+GFPP_API int gfpp_sr_forward(const gfpp_sr_model *model, uint32_t n_frames, uint32_t in_res, const float *rgb_in,
+                             const float *const noise[4], uint32_t noise_per_frame, float *out, int clamp01, void *workspace,
+                             size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

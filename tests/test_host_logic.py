@@ -194,6 +194,35 @@ def test_sr_head_matches_the_reference_golden():
         assert (net(full, noise_mode="none") - net(full, noise_mode="const")).abs().max().item() > 1e-4
 
 
+def test_sr_folded_weights_reproduce_the_fp32_head():
+    """Host half of the native SR path (superres.folded_weights: modulation + demodulation folded, transposed stride-2
+    convolution and its FIR merged into four 3x3 phase kernels) pushed through the CPU emulation of the kernels' data flow
+    (oracle/sr_emulate.py) must give the fp32 convolutions' image; with the kernels' fp16 operand rounding it must stay
+    inside the 1e-3 bar on the clamped image."""
+    import json
+    import os
+    from genefaceplusplus_b200.superres import Superresolution
+    from oracle.sr_emulate import emulate
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sr_head.npz"))
+    meta = json.loads(bytes(g["meta"]).decode())
+    net = Superresolution(channels=3).eval()
+    net.load_state_dict(scn.synthetic_sr_state({k: tuple(v) for k, v in meta["shapes"].items()}, seed=3), strict=False)
+    fw = net.folded_weights()
+    assert fw["up_w"].shape == (256, 1152) and fw["conv0_w"].shape == (128, 1152) and fw["conv1_w"].shape == (64, 576)
+    full = scn.hashed_uniform(3 * 256 * 256, 78, 1.0).reshape(1, 3, 256, 256) + 0.5
+    flat = full.permute(0, 2, 3, 1).reshape(1, -1, 3).contiguous()
+    with torch.no_grad():
+        nz = [(l.noise_const * l.noise_strength).float() for l in net._layers()]
+        ref = net(full, noise_mode="const")
+        e32 = (emulate(fw, flat, 256, nz, fp16=False) - ref).abs().max().item()
+        e16 = (emulate(fw, flat, 256, nz, fp16=True).clamp(0, 1) - ref.clamp(0, 1)).abs().max().item()
+    assert e32 < 1e-5, e32
+    assert e16 < 1e-3, e16
+    c0, c1, c2, c3 = meta["crop"]
+    crop = torch.from_numpy(g["in256_crop"])
+    assert (emulate(fw, flat, 256, nz, fp16=False)[0, :, c0:c1, c2:c3] - crop).abs().max().item() < 2e-5 * max(1.0, crop.abs().max().item())
+
+
 def test_sr_model_wraps_the_head_render(monkeypatch):
     """RADNeRFwithSR (radnerf_sr.py:203-210): extra state names, result keys and shapes -- with the NeRF render stubbed out
     (the real one needs the GPU and is covered by the head tests)."""
