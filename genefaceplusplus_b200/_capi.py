@@ -63,6 +63,21 @@ class SrModel(ctypes.Structure):
     _fields_ = [("opaque", ctypes.c_uint64 * 32)]
 
 
+class TorsoSrDesc(ctypes.Structure):
+    _fields_ = [("torso_grid", GridDesc), ("torso_deform_w", c_void_p * 3), ("torso_canon_w", c_void_p * 3), ("torso_code", c_void_p),
+                ("torso_code_dim", c_u32), ("head_aware", c_int), ("ha_w", c_void_p * 3), ("ha_b", c_void_p * 3),
+                ("density_grid_torso", c_void_p), ("grid_size", c_u32), ("density_thresh_torso", c_f), ("torso_shrink", c_f)]
+
+
+class TorsoSrModel(ctypes.Structure):
+    _fields_ = [("opaque", ctypes.c_uint64 * 128)]
+
+
+class TorsoSrFrames(ctypes.Structure):
+    _fields_ = [("n_frames", c_u32), ("n_rays", c_u32), ("image", c_void_p), ("weights_sum", c_void_p), ("lm68", c_void_p),
+                ("bg_coords", c_void_p), ("bg_color", c_void_p)]
+
+
 class Outputs(ctypes.Structure):
     _fields_ = [("rgb_map", c_void_p), ("depth_map", c_void_p), ("weights_sum", c_void_p),
                 ("torso_alpha_map", c_void_p), ("torso_rgb_map", c_void_p), ("torso_deform", c_void_p),
@@ -75,6 +90,7 @@ EXPORTS = [
     "gfpp_model_packed_bytes", "gfpp_model_pack", "gfpp_render_workspace_bytes", "gfpp_render_frames",
     "gfpp_last_launch_count", "gfpp_profile_enable", "gfpp_profile_read", "gfpp_profile_phases", "gfpp_tc_selftest", "gfpp_debug_generate_rays",
     "gfpp_sr_packed_bytes", "gfpp_sr_pack", "gfpp_sr_workspace_bytes", "gfpp_sr_forward",
+    "gfpp_torso_sr_packed_bytes", "gfpp_torso_sr_pack", "gfpp_torso_sr_workspace_bytes", "gfpp_torso_sr_composite",
 ]
 
 
@@ -113,6 +129,13 @@ def lib():
         L.gfpp_sr_workspace_bytes.argtypes = [c_u32, c_u32]
         L.gfpp_sr_forward.argtypes = [ctypes.POINTER(SrModel), c_u32, c_u32, c_void_p, ctypes.POINTER(c_void_p * 4), c_u32, c_void_p,
                                       c_int, c_void_p, c_size_t, c_void_p]
+        L.gfpp_torso_sr_packed_bytes.restype = c_size_t
+        L.gfpp_torso_sr_packed_bytes.argtypes = []
+        L.gfpp_torso_sr_pack.argtypes = [ctypes.POINTER(TorsoSrDesc), c_void_p, c_size_t, ctypes.POINTER(TorsoSrModel), c_void_p]
+        L.gfpp_torso_sr_workspace_bytes.restype = c_size_t
+        L.gfpp_torso_sr_workspace_bytes.argtypes = [c_u32]
+        L.gfpp_torso_sr_composite.argtypes = [ctypes.POINTER(TorsoSrModel), ctypes.POINTER(TorsoSrFrames), c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
         _lib = L
     return _lib
 

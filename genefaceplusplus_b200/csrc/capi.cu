@@ -12,6 +12,7 @@
 #include "launch.cuh"
 #include "sr_kernel.cuh"
 #include "torso_kernel.cuh"
+#include "torso_sr_kernel.cuh"
 
 namespace gfpp {
 // ops_kernels.cu
@@ -819,6 +820,152 @@ int gfpp_sr_forward(const gfpp_sr_model *model, uint32_t n_frames, uint32_t in_r
     a.noise = noise ? noise[3] : nullptr; a.noise_fstride = hi;
     a.rgb_w = m.rgb_w[1]; a.rgb_b = m.rgb_b[1]; a.img_in = (const float *)(ws + W.img0); a.img_out = out; a.clamp01 = clamp01;
     CK(launch_sr_conv(2, a, st));
+    return GFPP_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ (C) torso field of the torso-SR checkpoints (torso_sr_kernel.cu)
+namespace {
+struct TorsoSrHost {
+    uint32_t magic;
+    int head_aware;
+    GridMeta tor_gm;
+    const float2 *tor_tab;
+    const float *wd0, *wd1, *wd2, *wc0, *wc1, *wc2, *ha;
+    const float *def0_src, *can0_src, *code;     // originals (the per-frame bias fold reads them)
+    uint32_t code_dim;
+    const float *density_grid_torso;
+    uint32_t grid_size;
+    float density_thresh_torso, torso_shrink;
+};
+static_assert(sizeof(TorsoSrHost) <= sizeof(gfpp_torso_sr_model), "gfpp_torso_sr_model opaque storage too small");
+constexpr uint32_t kTorsoSrMagic = 0x67667473u;  // "gfts"
+struct TorsoSrPacked { size_t wd0, wd1, wd2, wc0, wc1, wc2, ha, total; };
+TorsoSrPacked torso_sr_packed_layout() {
+    TorsoSrPacked L;
+    size_t o = 0;
+    auto take = [&](size_t floats) { size_t r = o; o += (floats * 4 + 255) / 256 * 256; return r; };
+    L.wd0 = take(TORSO_SR_KD0 * 64); L.wd1 = take(64 * 64); L.wd2 = take(2 * 64);
+    L.wc0 = take(TORSO_SR_KC0 * 32); L.wc1 = take(32 * 32); L.wc2 = take(4 * 32);
+    L.ha = take(TORSO_SR_HA_FLOATS);
+    L.total = o;
+    return L;
+}
+struct TorsoSrWork { size_t bias_def, bias_can, pcount, total; };
+TorsoSrWork torso_sr_work_layout(uint32_t F) {
+    TorsoSrWork W;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
+    W.bias_def = take((size_t)F * 64 * 4);
+    W.bias_can = take((size_t)F * 32 * 4);
+    W.pcount = take((size_t)F * 4);
+    W.total = o;
+    return W;
+}
+__global__ void k_copy_ints(const int *src, int n, int32_t *dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+}  // namespace
+
+extern "C" {
+
+size_t gfpp_torso_sr_packed_bytes(void) { return torso_sr_packed_layout().total; }
+
+int gfpp_torso_sr_pack(const gfpp_torso_sr_desc *d, void *packed, size_t packed_bytes, gfpp_torso_sr_model *model, void *stream) {
+    if (!d || !packed || !model) return fail(GFPP_ERR_INVALID, "torso_sr_pack: null pointer%s");
+    const TorsoSrPacked L = torso_sr_packed_layout();
+    if (packed_bytes < L.total) return fail(GFPP_ERR_WORKSPACE, "torso_sr_pack: packed buffer too small%s");
+    for (int i = 0; i < 3; ++i)
+        if (!d->torso_deform_w[i] || !d->torso_canon_w[i]) return fail(GFPP_ERR_INVALID, "torso_sr_pack: null torso weight%s");
+    if (!d->density_grid_torso || !d->torso_grid.embeddings || !d->torso_grid.offsets_host) return fail(GFPP_ERR_INVALID, "torso_sr_pack: null grid%s");
+    if (d->torso_code_dim > 10 || (d->torso_code_dim > 0 && !d->torso_code)) return fail(GFPP_ERR_UNSUPPORTED, "torso_sr_pack: torso_code_dim <= 10 (with a code pointer)%s");
+    if (d->head_aware)
+        for (int i = 0; i < 3; ++i)
+            if (!d->ha_w[i] || !d->ha_b[i]) return fail(GFPP_ERR_INVALID, "torso_sr_pack: null head-aware encoder weight%s");
+    TorsoSrHost m;
+    memset(&m, 0, sizeof(m));
+    m.magic = kTorsoSrMagic;
+    if (d->torso_grid.num_levels != 16 ||
+        fill_grid_meta(m.tor_gm, d->torso_grid.offsets_host, d->torso_grid.input_dim, d->torso_grid.num_levels, d->torso_grid.log2_per_level_scale,
+                       d->torso_grid.base_resolution, d->torso_grid.gridtype, d->torso_grid.align_corners, d->torso_grid.interp) != 0 ||
+        m.tor_gm.dim != 2)
+        return fail(GFPP_ERR_UNSUPPORTED, "torso_sr_pack: the torso grid must be 2-D with 16 levels x 2 features%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *base = (char *)packed;
+    g_launches = 0;
+    CKN(cudaMemsetAsync(packed, 0, L.total, st));
+    const int ha = d->head_aware ? 1 : 0;
+    const int nh = (int)d->torso_code_dim + 126;
+    const int din = 42 + nh + (ha ? 16 : 0);
+    float *wd0 = (float *)(base + L.wd0), *wd1 = (float *)(base + L.wd1), *wd2 = (float *)(base + L.wd2);
+    float *wc0 = (float *)(base + L.wc0), *wc1 = (float *)(base + L.wc1), *wc2 = (float *)(base + L.wc2), *hab = (float *)(base + L.ha);
+    // input columns of the reference layers: deform [enc_x 42 | code | lm 126 | head-aware 16], canonical [grid 32 | the same]
+    CK(launch_pack_kmajor(d->torso_deform_w[0], din, 0, 0, 64, 42, 42, wd0, st));
+    CK(launch_pack_kmajor(d->torso_deform_w[0], din, 0, 42 + nh, 64, ha ? 16 : 0, 18, wd0 + 42 * 64, st));
+    CK(launch_pack_kmajor(d->torso_deform_w[1], 64, 0, 0, 64, 64, 64, wd1, st));
+    CK(launch_pack_rows(d->torso_deform_w[2], 64, 0, 2, 64, 64, wd2, st));
+    CK(launch_pack_kmajor(d->torso_canon_w[0], 32 + din, 0, 0, 32, 74, 74, wc0, st));
+    CK(launch_pack_kmajor(d->torso_canon_w[0], 32 + din, 0, 74 + nh, 32, ha ? 16 : 0, 18, wc0 + 74 * 32, st));
+    CK(launch_pack_kmajor(d->torso_canon_w[1], 32, 0, 0, 32, 32, 32, wc1, st));
+    CK(launch_pack_rows(d->torso_canon_w[2], 32, 0, 4, 32, 32, wc2, st));
+    if (ha) {
+        CK(launch_pack_kmajor(d->ha_w[0], 4, 0, 0, 16, 4, 4, hab + TORSO_SR_HA_W0, st));
+        CK(launch_pack_kmajor(d->ha_w[1], 16, 0, 0, 32, 16, 16, hab + TORSO_SR_HA_W1, st));
+        CK(launch_pack_kmajor(d->ha_w[2], 32, 0, 0, 16, 32, 32, hab + TORSO_SR_HA_W2, st));
+        CKN(cudaMemcpyAsync(hab + TORSO_SR_HA_B0, d->ha_b[0], 16 * 4, cudaMemcpyDeviceToDevice, st));
+        CKN(cudaMemcpyAsync(hab + TORSO_SR_HA_B1, d->ha_b[1], 32 * 4, cudaMemcpyDeviceToDevice, st));
+        CKN(cudaMemcpyAsync(hab + TORSO_SR_HA_B2, d->ha_b[2], 16 * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    m.head_aware = ha;
+    m.tor_tab = (const float2 *)d->torso_grid.embeddings;
+    m.wd0 = wd0; m.wd1 = wd1; m.wd2 = wd2; m.wc0 = wc0; m.wc1 = wc1; m.wc2 = wc2; m.ha = ha ? hab : nullptr;
+    m.def0_src = d->torso_deform_w[0]; m.can0_src = d->torso_canon_w[0]; m.code = d->torso_code; m.code_dim = d->torso_code_dim;
+    m.density_grid_torso = d->density_grid_torso; m.grid_size = d->grid_size;
+    m.density_thresh_torso = d->density_thresh_torso; m.torso_shrink = d->torso_shrink;
+    memset(model, 0, sizeof(*model));
+    memcpy(model, &m, sizeof(m));
+    return GFPP_OK;
+}
+
+size_t gfpp_torso_sr_workspace_bytes(uint32_t n_frames) { return torso_sr_work_layout(n_frames).total; }
+
+int gfpp_torso_sr_composite(const gfpp_torso_sr_model *model, const gfpp_torso_sr_frames *fr, float *rgb_map, float *torso_alpha_map,
+                            float *torso_rgb_map, float *torso_deform, int32_t *torso_pixels, void *workspace, size_t workspace_bytes,
+                            void *stream) {
+    if (!model || !fr || !rgb_map || !workspace) return fail(GFPP_ERR_INVALID, "torso_sr_composite: null pointer%s");
+    TorsoSrHost m;
+    memcpy(&m, model, sizeof(m));
+    if (m.magic != kTorsoSrMagic) return fail(GFPP_ERR_INVALID, "torso_sr_composite: model handle not initialised by gfpp_torso_sr_pack%s");
+    if (!fr->image || !fr->weights_sum || !fr->lm68 || !fr->bg_coords) return fail(GFPP_ERR_INVALID, "torso_sr_composite: image, weights_sum, lm68 and bg_coords are required%s");
+    if (fr->n_frames == 0 || fr->n_rays == 0) return fail(GFPP_ERR_INVALID, "torso_sr_composite: empty clip%s");
+    if ((uint64_t)fr->n_frames * fr->n_rays >= (1ull << 31)) return fail(GFPP_ERR_UNSUPPORTED, "torso_sr_composite: F*N must be < 2^31%s");
+    const TorsoSrWork W = torso_sr_work_layout(fr->n_frames);
+    if (workspace_bytes < W.total) return fail(GFPP_ERR_WORKSPACE, "torso_sr_composite: workspace too small%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    g_launches = 0;
+    CKN(cudaMemsetAsync(ws + W.pcount, 0, (size_t)fr->n_frames * 4, st));
+    CK(launch_torso_sr_frame_bias(fr->lm68, (int)fr->n_frames, m.def0_src, m.can0_src, m.code, (int)m.code_dim, m.head_aware,
+                                  (float *)(ws + W.bias_def), (float *)(ws + W.bias_can), st));
+    TorsoSrArgs t;
+    memset(&t, 0, sizeof(t));
+    t.tor_gm = m.tor_gm; t.tor_tab = m.tor_tab;
+    t.w_def0 = m.wd0; t.w_def1 = m.wd1; t.w_def2 = m.wd2; t.w_can0 = m.wc0; t.w_can1 = m.wc1; t.w_can2 = m.wc2; t.ha = m.ha;
+    t.bias_def = (const float *)(ws + W.bias_def); t.bias_can = (const float *)(ws + W.bias_can);
+    t.density_grid_torso = m.density_grid_torso; t.grid_size = (int)m.grid_size;
+    t.density_thresh_torso = m.density_thresh_torso; t.torso_shrink = m.torso_shrink;
+    t.bg_coords = fr->bg_coords; t.bg_color = fr->bg_color;
+    t.n_frames = (int)fr->n_frames; t.n_rays = (int)fr->n_rays;
+    t.image = fr->image; t.wsum = fr->weights_sum;
+    t.rgb_map = rgb_map; t.torso_alpha = torso_alpha_map; t.torso_rgb = torso_rgb_map; t.deform = torso_deform;
+    t.P_count = (int *)(ws + W.pcount);
+    CK(launch_torso_sr(t, st));
+    if (torso_pixels) {
+        k_copy_ints<<<(fr->n_frames + 127) / 128, 128, 0, st>>>(t.P_count, (int)fr->n_frames, torso_pixels);
+        CK(cudaGetLastError());
+    }
     return GFPP_OK;
 }
 

@@ -591,6 +591,8 @@ class RADNeRFTorsowithSR(RADNeRF):
     has_torso = False            # what gets packed for libgfpp is the head field only
     forwards_eye_area = True     # radnerf_torso_sr.py:136
     sr_input_resolution = 256
+    torso_backend = "torch"      # FLIP-AFTER-GPU-VALIDATION -> "native": libgfpp's k_torso_sr (csrc/torso_sr_kernel.cu); "torch":
+                                 # the host-side field below over libgfpp's per-op encoder kernels (the first correct path)
 
     def __init__(self, hparams):
         super().__init__(hparams)
@@ -647,6 +649,102 @@ class RADNeRFTorsowithSR(RADNeRF):
         h = self._mlp(torch.cat([xf, h], dim=-1), self.torso_canonicial_net)
         return torch.sigmoid(h[..., :1]), torch.sigmoid(h[..., 1:]), dx
 
+    def _torso_native_state(self):
+        """gfpp_torso_sr_pack once per (device, parameter versions)."""
+        dev = self.density_bitfield.device
+        ts = [self.density_grid_torso, self.torso_embedder.embeddings] + [l.weight for l in self.torso_deform_net.net] + \
+             [l.weight for l in self.torso_canonicial_net.net]
+        if self.torso_individual_embedding_dim > 0:
+            ts.append(self.torso_individual_codes)
+        if self.torso_head_aware:
+            ts += [p for p in self.head_color_weights_encoder.parameters()]
+        thr = float(min(self.density_thresh_torso, self.mean_density_torso))
+        key = (dev.index, thr, tuple((t.data_ptr(), int(t._version)) for t in ts))
+        st = self.__dict__.get("_torso_native")
+        if st is not None and st["key"] == key:
+            return st
+        L = _capi.lib()
+        keep = []
+        d = _capi.TorsoSrDesc()
+        d.torso_grid = self._grid_desc(self.torso_embedder, keep)
+        for i in range(3):
+            d.torso_deform_w[i] = self._w(self.torso_deform_net.net[i].weight, keep)
+            d.torso_canon_w[i] = self._w(self.torso_canonicial_net.net[i].weight, keep)
+        d.torso_code_dim = self.torso_individual_embedding_dim
+        if self.torso_individual_embedding_dim > 0:
+            d.torso_code = self._w(self.torso_individual_codes[0], keep)        # eval uses code 0 (radnerf_torso_sr.py:188)
+        d.head_aware = int(self.torso_head_aware)
+        if self.torso_head_aware:
+            lins = [m for m in self.head_color_weights_encoder if isinstance(m, nn.Linear)]
+            for i, lin in enumerate(lins):
+                d.ha_w[i] = self._w(lin.weight, keep)
+                d.ha_b[i] = self._w(lin.bias, keep)
+        g = self.density_grid_torso
+        keep.append(g)
+        d.density_grid_torso = g.data_ptr()
+        d.grid_size = self.grid_size
+        d.density_thresh_torso = thr
+        d.torso_shrink = float(self.torso_shrink)
+        packed = torch.empty(L.gfpp_torso_sr_packed_bytes(), dtype=torch.uint8, device=dev)
+        model = _capi.TorsoSrModel()
+        with torch.cuda.device(dev):
+            _capi.check(L.gfpp_torso_sr_pack(ctypes.byref(d), packed.data_ptr(), packed.numel(), ctypes.byref(model), _capi.stream_ptr(dev)),
+                        "gfpp_torso_sr_pack")
+        st = {"key": key, "packed": packed, "model": model, "keep": keep, "ws": None}
+        self.__dict__["_torso_native"] = st
+        return st
+
+    def torso_composite_native(self, image, weights_sum, lm68, bg_coords, bg_color=None, want_maps=True, rgb_out=None):
+        """Torso field + three-way composite of F frames in libgfpp (k_torso_sr): image [F,N,3] premultiplied head colour,
+        weights_sum [F,N], lm68 [F,136], bg_coords [N,2], bg_color [N,3] / None (= 1).  Returns a dict of device tensors:
+        rgb_map [F,N,3] (clamped) and, want_maps, torso_alpha_map [F,N], torso_rgb_map [F,N,3], deform [F,N,2], torso_pixels [F]."""
+        dev = self.density_bitfield.device
+        if dev.type != "cuda":
+            raise _capi.GfppError("model is not on a CUDA device: libgfpp has no CPU path (call .cuda())")
+        f32 = torch.float32
+        st = self._torso_native_state()
+        L = _capi.lib()
+        image = image.to(dev, f32).contiguous()
+        Fn, N = image.shape[0], image.shape[1]
+        weights_sum = weights_sum.to(dev, f32).reshape(Fn, N).contiguous()
+        lm68 = lm68.to(dev, f32).reshape(Fn, 136).contiguous()
+        bg_coords = bg_coords.to(dev, f32).reshape(-1, 2).contiguous()
+        if bg_coords.shape[0] != N:
+            raise ValueError(f"bg_coords must be [{N},2] (one row per pixel)")
+        fr = _capi.TorsoSrFrames()
+        fr.n_frames, fr.n_rays = Fn, N
+        fr.image, fr.weights_sum, fr.lm68, fr.bg_coords = image.data_ptr(), weights_sum.data_ptr(), lm68.data_ptr(), bg_coords.data_ptr()
+        hold = [image, weights_sum, lm68, bg_coords]
+        if bg_color is not None:
+            if not torch.is_tensor(bg_color):
+                bg_color = torch.full((N, 3), float(bg_color), device=dev, dtype=f32)
+            bg_color = bg_color.to(dev, f32).reshape(-1, 3)
+            if bg_color.shape[0] == 1:
+                bg_color = bg_color.expand(N, 3)
+            elif bg_color.shape[0] != N:
+                raise ValueError(f"bg_color must have 1 or {N} rows, got {bg_color.shape[0]}")
+            bg_color = bg_color.contiguous()
+            fr.bg_color = bg_color.data_ptr()
+            hold.append(bg_color)
+        res = {"rgb_map": rgb_out if rgb_out is not None else torch.empty(Fn, N, 3, device=dev, dtype=f32)}
+        if res["rgb_map"].dtype != f32 or not res["rgb_map"].is_contiguous() or res["rgb_map"].numel() != Fn * N * 3:
+            raise ValueError(f"rgb_out must be a contiguous fp32 [{Fn},{N},3] tensor")
+        ptrs = [None] * 4
+        if want_maps:
+            res["torso_alpha_map"] = torch.empty(Fn, N, device=dev, dtype=f32)
+            res["torso_rgb_map"] = torch.empty(Fn, N, 3, device=dev, dtype=f32)
+            res["deform"] = torch.empty(Fn, N, 2, device=dev, dtype=f32)
+            res["torso_pixels"] = torch.empty(Fn, device=dev, dtype=torch.int32)
+            ptrs = [res[k].data_ptr() for k in ("torso_alpha_map", "torso_rgb_map", "deform", "torso_pixels")]
+        need = L.gfpp_torso_sr_workspace_bytes(Fn)
+        if st["ws"] is None or st["ws"].numel() < need:
+            st["ws"] = torch.empty(need, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _capi.check(L.gfpp_torso_sr_composite(ctypes.byref(st["model"]), ctypes.byref(fr), res["rgb_map"].data_ptr(), *ptrs,
+                                                  st["ws"].data_ptr(), st["ws"].numel(), _capi.stream_ptr(dev)), "gfpp_torso_sr_composite")
+        del hold
+        return res
+
     def _head(self, rays_o, rays_d, cond_feat, dt_gamma, max_steps, T_thresh):
         """Premultiplied head colour, alpha and normalised depth of one frame from libgfpp (background 0 => rgb_map == image)."""
         N = rays_o.numel() // 3
@@ -679,9 +777,22 @@ class RADNeRFTorsowithSR(RADNeRF):
             G = self.grid_size
             occ = F.grid_sample(self.density_grid_torso.view(1, 1, G, G), bg_coords.view(1, -1, 1, 2), align_corners=True).view(-1)
             mask = occ > min(self.density_thresh_torso, self.mean_density_torso)
+            results = {}
+            noise_mode = kwargs.get("sr_noise_mode", "random")
+            if self.torso_backend == "native":
+                tr = self.torso_composite_native(image.view(1, N, 3), weights_sum.view(1, N), lm68.reshape(1, 136), bg_coords,
+                                                 None if not torch.is_tensor(bg) and bg == 1 else bg)
+                if bool(mask.any()):
+                    results["deform"] = tr["deform"][0][mask]
+                rgb_image = tr["rgb_map"].view(1, R, R, 3).permute(0, 3, 1, 2)
+                torso_bg = tr["torso_rgb_map"].view(1, R, R, 3).permute(0, 3, 1, 2)
+                results.update({"torso_alpha_map": tr["torso_alpha_map"].view(N, 1), "torso_rgb_map": torso_bg, "depth_map": depth.view(*prefix),
+                                "rgb_map": rgb_image, "sr_rgb_map": self.sr_net(rgb_image, noise_mode=noise_mode).clamp(0, 1)})
+                if upscale_torso:
+                    results["sr_torso_rgb_map"] = self.sr_net(torso_bg, noise_mode=noise_mode).clamp(0, 1)
+                return results
             torso_alpha = torch.zeros(N, 1, device=dev)
             torso_color = torch.zeros(N, 3, device=dev)
-            results = {}
             if bool(mask.any()):
                 a, c, deform = self.forward_torso(bg_coords[mask], poses, code, image[mask] if self.torso_head_aware else None,
                                                   weights_sum.unsqueeze(-1)[mask] if self.torso_head_aware else None, lm68=lm68)
@@ -692,7 +803,6 @@ class RADNeRFTorsowithSR(RADNeRF):
             img = (image + (1 - weights_sum).unsqueeze(-1) * torso_bg).clamp(0, 1)
             rgb_image = img.reshape(1, R, R, 3).permute(0, 3, 1, 2)
             torso_bg = torso_bg.reshape(1, R, R, 3).permute(0, 3, 1, 2)
-            noise_mode = kwargs.get("sr_noise_mode", "random")
             results.update({"torso_alpha_map": torso_alpha, "torso_rgb_map": torso_bg, "depth_map": depth.view(*prefix),
                             "rgb_map": rgb_image, "sr_rgb_map": self.sr_net(rgb_image, noise_mode=noise_mode).clamp(0, 1)})
             if upscale_torso:
@@ -713,6 +823,23 @@ class RADNeRFTorsowithSR(RADNeRF):
         T = poses_c2w.shape[0]
         dev = self.density_bitfield.device
         out = torch.empty(T, 3, 2 * R, 2 * R, device=dev, dtype=torch.float32)
+        if self.torso_backend == "native" and self.sr_net.backend == "native":
+            # everything in libgfpp, chunk by chunk: head field (rays generated in-kernel, background 0 => premultiplied colour),
+            # torso-SR field + composite, SR head; no per-frame host work
+            fpc = int(unused.get("frames_per_call", 8))
+            cond_feat = self.cal_cond_feat_clip(cond_seq.to(dev), eye_area_percent=eye_area_percent)
+            poses_c2w = poses_c2w.to(dev, torch.float32)
+            zero_bg = torch.zeros(R * R, 3, device=dev)
+            with torch.autocast(dev.type, enabled=False):
+                for s in range(0, T, fpc):
+                    e = min(T, s + fpc)
+                    hd = self.render_frames(cond_feat[s:e], poses_c2w=poses_c2w[s:e], intrinsics=intrinsics, H=H, W=W, bg_color=zero_bg,
+                                            dt_gamma=hp["dt_gamma"] if dt_gamma is None else dt_gamma,
+                                            max_steps=hp["max_steps"] if max_steps is None else max_steps, T_thresh=T_thresh)
+                    tr = self.torso_composite_native(hd["rgb_map"], hd["weights_sum"], lm68_seq[s:e].reshape(e - s, 136), bg_coords, bg_color,
+                                                     want_maps=False)
+                    self.sr_net.forward_native(tr["rgb_map"], noise_mode=sr_noise_mode, clamp=True, out=out[s:e], frames_per_call=fpc)
+            return out
         for t in range(T):
             rays_o, rays_d = get_rays(poses_c2w[t].cpu(), intrinsics, H, W)
             res = self.render(rays_o.to(dev), rays_d.to(dev), cond_window(cond_seq, t, self.smo_win_size).to(dev), bg_coords,

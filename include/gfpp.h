@@ -258,6 +258,55 @@ GFPP_API int gfpp_sr_forward(const gfpp_sr_model *model, uint32_t n_frames, uint
                              const float *const noise[4], uint32_t noise_per_frame, float *out, int clamp01, void *workspace,
                              size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------ (C) torso field of the torso-SR checkpoints
+ *
+ * Replaces RADNeRFTorsowithSR.forward_torso + the composite of its render() (modules/radnerfs/radnerf_torso_sr.py:75-113,
+ * 196-228): mask by grid_sample of density_grid_torso, the landmark-conditioned (and, `torso_head_aware`, head-colour-aware)
+ * deformation + canonical torso field on the masked pixels, torso over background, head over both, clamp.  The head NeRF of
+ * these checkpoints is the plain head field: render it with gfpp_render_frames (has_torso = 0, bg_color = zeros, so that
+ * `rgb_map` is the premultiplied head colour and `weights_sum` its alpha) and hand both over here; the result feeds
+ * gfpp_sr_forward.  Weights in the reference's nn.Linear layout [out, in], fp32 device pointers (state_dict tensors); the
+ * grid table, density_grid_torso, the first deform / canonical layers and the code are BORROWED (per-frame folds read them). */
+typedef struct {
+    gfpp_grid_desc torso_grid;          /* 2-D tiled grid, 16 levels x 2 */
+    const float *torso_deform_w[3];     /* (64,din) (64,64) (2,64); din = 42 + torso_code_dim + 126 (+ 16 if head_aware) */
+    const float *torso_canon_w[3];      /* (32,32+din) (32,32) (4,32) */
+    const float *torso_code;            /* [torso_code_dim] = torso_individual_codes[0] */
+    uint32_t torso_code_dim;            /* 8 */
+    int head_aware;                     /* hparams['torso_head_aware'] */
+    const float *ha_w[3];               /* head_color_weights_encoder: (16,4) (32,16) (16,32) */
+    const float *ha_b[3];               /* its biases: 16, 32, 16 */
+    const float *density_grid_torso;    /* [grid_size^2] */
+    uint32_t grid_size;
+    float density_thresh_torso;         /* min(density_thresh_torso, mean_density_torso) as the reference evaluates it */
+    float torso_shrink;
+} gfpp_torso_sr_desc;
+
+typedef struct gfpp_torso_sr_model {
+    uint64_t opaque[128];
+} gfpp_torso_sr_model;
+
+typedef struct {
+    uint32_t n_frames;            /* F */
+    uint32_t n_rays;              /* N pixels per frame (256*256 in the reference) */
+    const float *image;           /* [F,N,3] premultiplied head colour */
+    const float *weights_sum;     /* [F,N]   head alpha */
+    const float *lm68;            /* [F,136] 68 2-D landmarks per frame (points 5..11 = the jaw are used) */
+    const float *bg_coords;       /* [N,2]   shared by all frames */
+    const float *bg_color;        /* [N,3]   shared by all frames, or NULL => 1.0 */
+} gfpp_torso_sr_frames;
+
+GFPP_API size_t gfpp_torso_sr_packed_bytes(void);
+GFPP_API int gfpp_torso_sr_pack(const gfpp_torso_sr_desc *desc, void *packed, size_t packed_bytes, gfpp_torso_sr_model *model,
+                                void *stream);
+GFPP_API size_t gfpp_torso_sr_workspace_bytes(uint32_t n_frames);
+/* rgb_map [F,N,3] (required): the clamped composite; torso_alpha_map [F,N], torso_rgb_map [F,N,3] (torso over background),
+ * torso_deform [F,N,2] (0 outside the mask), torso_pixels [F] (masked pixels per frame): optional, NULL to skip.
+ * Two kernel launches, no host sync, no allocation. */
+GFPP_API int gfpp_torso_sr_composite(const gfpp_torso_sr_model *model, const gfpp_torso_sr_frames *frames, float *rgb_map,
+                                     float *torso_alpha_map, float *torso_rgb_map, float *torso_deform, int32_t *torso_pixels,
+                                     void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

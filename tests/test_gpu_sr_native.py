@@ -88,3 +88,72 @@ def test_native_sr_repacks_when_a_parameter_changes():
     b = net.forward_native(flat[:1].cuda(), noise_mode="none")
     torch.cuda.synchronize()
     assert (a - b).abs().max().item() > 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ torso-SR field in libgfpp
+def _torso_sr(head_aware):
+    from genefaceplusplus_b200.config import may_hparams
+    from genefaceplusplus_b200.renderer import RADNeRFTorsowithSR
+    z = np.load(os.path.join(GOLD, "torso_sr256.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    hp = may_hparams(**{**meta["overrides"], "torso_head_aware": head_aware})
+    m = RADNeRFTorsowithSR(hp)
+    m.load_state_dict(scn.make_torso_sr_state(hp), strict=True)
+    m.density_scale = meta["density_scale"]
+    m = m.cuda().eval()
+    sc = scn.Scene(H=256, W=256, T=8, torso=True, density_scale=meta["density_scale"])
+    return m, hp, sc, z, meta
+
+
+def _render(m, hp, sc, meta, t, **extra):
+    fi = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in sc.frame_inputs(t).items()}
+    lm68 = scn.lm68_sequence(8)[t].reshape(1, 136).cuda()
+    kw = {k: v for k, v in hp.items() if k not in ("max_steps", "dt_gamma")}
+    return m.render(fi["rays_o"], fi["rays_d"], scn.cond_window(sc.cond, t, 3).cuda(), fi["bg_coords"], fi["poses"], index=t,
+                    dt_gamma=hp["dt_gamma"], bg_color=fi["bg_color"], max_steps=16, T_thresh=sc.T_thresh, upscale_torso=True, lm68=lm68,
+                    eye_area_percent=torch.tensor([[meta["eye"]]]), sr_noise_mode="const", **kw, **extra)
+
+
+@pytest.mark.parametrize("head_aware", [True, False])
+def test_torso_sr_field_native_matches_the_host_path(head_aware):
+    """k_torso_sr (libgfpp) against the host-side torch field over the per-op encoder kernels -- itself pinned to the reference's
+    render() golden (tests/test_gpu_sr.py) -- on the same head image: fp32 both, so 1e-5 on every map."""
+    m, hp, sc, z, meta = _torso_sr(head_aware)
+    m.sr_net.backend = "torch"
+    t = meta["frame"]
+    m.torso_backend = "torch"
+    ref = _render(m, hp, sc, meta, t)
+    m.torso_backend = "native"
+    got = _render(m, hp, sc, meta, t)
+    torch.cuda.synchronize()
+    for k in ("rgb_map", "torso_rgb_map", "torso_alpha_map", "deform", "sr_rgb_map"):
+        e = (got[k].float() - ref[k].float()).abs().max().item()
+        print(f"head_aware={head_aware} {k}: |native - host| = {e:.3e}")
+        assert got[k].shape == ref[k].shape and e <= (2e-5 if k != "sr_rgb_map" else 2e-4), (k, e)
+    if head_aware:   # the golden was made with torso_head_aware=True: the reference's own render()
+        for k, (a, b, c, d) in meta["crops"].items():
+            e = (got[k][0, :, a:b, c:d].float().cpu() - torch.from_numpy(z[f"{k}_crop"])).abs().max().item()
+            print(f"{k}: |native - reference golden| = {e:.3e}")
+            assert e <= 1e-3, (k, e)
+        assert abs(got["torso_alpha_map"].double().sum().item() - float(z["torso_alpha_sum"][0])) < 1.0
+
+
+def test_torso_sr_clip_all_native_matches_per_frame_render():
+    """render_clip with every stage in libgfpp (head field with in-kernel rays, torso-SR field, SR head) against per-frame
+    render() with the host-side torso field and fp32 SR convolutions."""
+    m, hp, sc, z, meta = _torso_sr(True)
+    T = 3
+    m.torso_backend, m.sr_net.backend = "torch", "torch"
+    ref = torch.stack([_render(m, hp, sc, meta, t)["sr_rgb_map"][0] for t in range(T)])
+    m.torso_backend, m.sr_net.backend = "native", "native"
+    poses = torch.stack([sc.pose(t) for t in range(T)]).cuda()
+    eye = torch.full((8,), meta["eye"])   # conditioning of the whole 8-frame sequence: same windows as cond_window(sc.cond, t, 3)
+    got = m.render_clip(poses, sc.intrinsics, 256, 256, cond_seq=sc.cond.cuda(), bg_color=sc.bg_color.cuda(), bg_coords=sc.bg_coords.cuda(),
+                        lm68_seq=scn.lm68_sequence(8)[:T].cuda(), eye_area_percent=eye, max_steps=16, T_thresh=sc.T_thresh, sr_noise_mode="const",
+                        frames_per_call=2)
+    torch.cuda.synchronize()
+    d = (got - ref).abs()
+    frac = (d > 1e-3).float().mean().item()   # in-kernel rays differ from get_rays by <= 2 ulp: rare occupancy-cell flips (DESIGN 6)
+    psnr = 10 * np.log10(1.0 / max(d.square().mean().item(), 1e-20))
+    print(f"torso-SR clip, all native: max {d.max().item():.3e}, fraction > 1e-3: {frac:.2e}, PSNR {psnr:.1f} dB")
+    assert frac <= 1e-4 and psnr >= 50.0
