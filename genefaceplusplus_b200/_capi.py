@@ -91,6 +91,9 @@ EXPORTS = [
     "gfpp_last_launch_count", "gfpp_profile_enable", "gfpp_profile_read", "gfpp_profile_phases", "gfpp_tc_selftest", "gfpp_debug_generate_rays",
     "gfpp_sr_packed_bytes", "gfpp_sr_pack", "gfpp_sr_workspace_bytes", "gfpp_sr_forward",
     "gfpp_torso_sr_packed_bytes", "gfpp_torso_sr_pack", "gfpp_torso_sr_workspace_bytes", "gfpp_torso_sr_composite",
+    "gfpp_march_rays_train_scratch_bytes", "gfpp_march_rays_train", "gfpp_march_rays_train_backward", "gfpp_composite_rays_train_forward",
+    "gfpp_composite_rays_train_backward", "gfpp_grid_encode_forward_dydx", "gfpp_grid_encode_backward", "gfpp_grad_total_variation",
+    "gfpp_packbits", "gfpp_morton3D", "gfpp_morton3D_invert", "gfpp_morton3D_dilation", "gfpp_sph_from_ray",
 ]
 
 
@@ -136,6 +139,21 @@ def lib():
         L.gfpp_torso_sr_workspace_bytes.argtypes = [c_u32]
         L.gfpp_torso_sr_composite.argtypes = [ctypes.POINTER(TorsoSrModel), ctypes.POINTER(TorsoSrFrames), c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+        P = c_void_p
+        L.gfpp_march_rays_train_scratch_bytes.restype = c_size_t
+        L.gfpp_march_rays_train_scratch_bytes.argtypes = [c_u32]
+        L.gfpp_march_rays_train.argtypes = [P, P, P, c_f, c_f, c_u32, c_u32, c_u32, c_u32, c_u32, P, P, P, P, P, P, P, P, P, c_size_t, P]
+        L.gfpp_march_rays_train_backward.argtypes = [P, P, P, P, c_u32, c_u32, P, P, P]
+        L.gfpp_composite_rays_train_forward.argtypes = [P, P, P, P, P, c_u32, c_u32, c_f, P, P, P, P, P]
+        L.gfpp_composite_rays_train_backward.argtypes = [P, P, P, P, P, P, P, P, P, P, P, c_u32, c_u32, c_f, P, P, P, P]
+        L.gfpp_grid_encode_forward_dydx.argtypes = [P, P, P, P, c_u32, c_u32, c_u32, c_u32, c_f, c_u32, P, c_u32, c_int, c_u32, P]
+        L.gfpp_grid_encode_backward.argtypes = [P, P, P, P, P, c_u32, c_u32, c_u32, c_u32, c_f, c_u32, P, P, c_u32, c_int, c_u32, P]
+        L.gfpp_grad_total_variation.argtypes = [P, P, P, P, c_f, c_u32, c_u32, c_u32, c_u32, c_f, c_u32, c_u32, c_int, P]
+        L.gfpp_packbits.argtypes = [P, c_u32, c_f, P, P]
+        L.gfpp_morton3D.argtypes = [P, c_u32, P, P]
+        L.gfpp_morton3D_invert.argtypes = [P, c_u32, P, P]
+        L.gfpp_morton3D_dilation.argtypes = [P, c_u32, c_u32, P, P]
+        L.gfpp_sph_from_ray.argtypes = [P, P, c_f, c_u32, P, P]
         _lib = L
     return _lib
 

@@ -3,8 +3,11 @@ imports its CUDA extensions by -- `_raymarching_face`, `_gridencoder`, `_shencod
 (modules/radnerfs/raymarching/raymarching.py:9-12, encoders/*/: `try: import _x as _backend`) -- so the UNMODIFIED reference
 wrappers run on libgfpp's per-op kernels.  Call `install()` before `import modules.radnerfs`.
 
-Only the inference exports exist (near_far_from_aabb, march_rays, composite_rays, grid_encode_forward, sh_encode_forward,
-freq_encode_forward); training-only functions raise, exactly because they are out of scope.
+Inference exports: near_far_from_aabb, march_rays, composite_rays, grid_encode_forward, sh_encode_forward, freq_encode_forward.
+Training-side exports (csrc/train_kernels.cu): march_rays_train(+_backward), composite_rays_train_forward /
+_backward, grid_encode_forward with dy_dx, grid_encode_backward, grad_total_variation, packbits, morton3D(+_invert, _dilation),
+sph_from_ray -- fp32 (run them with autocast disabled).  The input-gradient ops of the SH / frequency encoders (only needed when
+optimising camera poses through the view direction) still raise.
 """
 import ctypes
 import sys
@@ -70,24 +73,63 @@ def make_modules():
     rm.composite_rays = lambda n_alive, n_step, T_thresh, alive, t, sig, rgb, deltas, ws, depth, image: _ck(
         L.gfpp_composite_rays(n_alive, n_step, cf(T_thresh), _P(alive), _P(t), _P(sig), _P(rgb), _P(deltas), _P(ws), _P(depth), _P(image), S()),
         "composite_rays")
-    for n in ("packbits", "sph_from_ray", "morton3D", "morton3D_invert", "morton3D_dilation", "march_rays_train", "march_rays_train_backward",
-              "composite_rays_train_forward", "composite_rays_train_backward"):
-        setattr(rm, n, _training_only(n))
+    # ---- training side (raymarching.h:8-17) ----
+    scratch = {}
+
+    def march_rays_train(ro, rd, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter, noises):
+        need = L.gfpp_march_rays_train_scratch_bytes(N)
+        key = ro.device.index
+        if key not in scratch or scratch[key].numel() < need:
+            scratch[key] = torch.empty(need, dtype=torch.uint8, device=ro.device)
+        _ck(L.gfpp_march_rays_train(_P(ro), _P(rd), _P(grid), cf(bound), cf(dt_gamma), max_steps, N, C, H, M, _P(nears), _P(fars), _P(xyzs),
+                                    _P(dirs), _P(deltas), _P(rays), _P(counter), _P(noises), _P(scratch[key]), scratch[key].numel(), S()),
+            "march_rays_train")
+
+    rm.march_rays_train = march_rays_train
+    rm.march_rays_train_backward = lambda gx, gd, rays, deltas, N, M, gro, grd: _ck(
+        L.gfpp_march_rays_train_backward(_P(gx), _P(gd), _P(rays), _P(deltas), N, M, _P(gro), _P(grd), S()), "march_rays_train_backward")
+    rm.composite_rays_train_forward = lambda sig, rgb, amb, deltas, rays, M, N, T_thresh, ws, asum, depth, image: _ck(
+        L.gfpp_composite_rays_train_forward(_P(sig), _P(rgb), _P(amb), _P(deltas), _P(rays), M, N, cf(T_thresh), _P(ws), _P(asum), _P(depth),
+                                            _P(image), S()), "composite_rays_train_forward")
+    rm.composite_rays_train_backward = lambda gws, gas, gimg, sig, rgb, amb, deltas, rays, ws, asum, image, M, N, T_thresh, gsig, grgb, gamb: _ck(
+        L.gfpp_composite_rays_train_backward(_P(gws), _P(gas), _P(gimg), _P(sig), _P(rgb), _P(amb), _P(deltas), _P(rays), _P(ws), _P(asum),
+                                             _P(image), M, N, cf(T_thresh), _P(gsig), _P(grgb), _P(gamb), S()), "composite_rays_train_backward")
+    rm.packbits = lambda grid, N, thresh, bitfield: _ck(L.gfpp_packbits(_P(grid), N, cf(thresh), _P(bitfield), S()), "packbits")
+    rm.morton3D = lambda coords, N, indices: _ck(L.gfpp_morton3D(_P(coords), N, _P(indices), S()), "morton3D")
+    rm.morton3D_invert = lambda indices, N, coords: _ck(L.gfpp_morton3D_invert(_P(indices), N, _P(coords), S()), "morton3D_invert")
+    rm.morton3D_dilation = lambda grid, C, H, out: _ck(L.gfpp_morton3D_dilation(_P(grid), C, H, _P(out), S()), "morton3D_dilation")
+    rm.sph_from_ray = lambda ro, rd, radius, N, coords: _ck(L.gfpp_sph_from_ray(_P(ro), _P(rd), cf(radius), N, _P(coords), S()), "sph_from_ray")
 
     ge = types.ModuleType("_gridencoder")
 
     def grid_encode_forward(inputs, emb, offsets, outputs, B, D, C, Lv, S_, H, dy_dx, gridtype, align_corners, interp):
-        if dy_dx is not None:
-            raise NotImplementedError("grid_encode_forward with dy_dx is a training path")
         if emb.dtype != torch.float32:
             raise RuntimeError("libgfpp grid tables are fp32 (run the encoder with autocast disabled)")
         off = _offsets_host(offsets)
+        if dy_dx is not None:   # calc_grad_inputs (grid.py:49-52): the ambient grid's input comes out of the ambient net
+            _ck(L.gfpp_grid_encode_forward_dydx(_P(inputs, torch.float32), _P(emb), off.ctypes.data_as(ctypes.c_void_p), _P(outputs, torch.float32),
+                                                B, D, C, Lv, cf(S_), H, _P(dy_dx, torch.float32), gridtype, int(align_corners), interp, S()),
+                "grid_encode_forward")
+            return
         _ck(L.gfpp_grid_encode_forward(_P(inputs, torch.float32), _P(emb), off.ctypes.data_as(ctypes.c_void_p), _P(outputs, torch.float32), B, D, C, Lv, cf(S_), H, gridtype,
                                        int(align_corners), interp, S()), "grid_encode_forward")
 
     ge.grid_encode_forward = grid_encode_forward
-    ge.grid_encode_backward = _training_only("grid_encode_backward")
-    ge.grad_total_variation = _training_only("grad_total_variation")
+
+    def grid_encode_backward(grad, inputs, emb, offsets, grad_emb, B, D, C, Lv, S_, H, dy_dx, grad_inputs, gridtype, align_corners, interp):
+        off = _offsets_host(offsets)
+        _ck(L.gfpp_grid_encode_backward(_P(grad, torch.float32), _P(inputs, torch.float32), _P(emb, torch.float32), off.ctypes.data_as(ctypes.c_void_p),
+                                        _P(grad_emb, torch.float32), B, D, C, Lv, cf(S_), H, None if dy_dx is None else _P(dy_dx, torch.float32),
+                                        None if grad_inputs is None else _P(grad_inputs, torch.float32), gridtype, int(align_corners), interp, S()),
+            "grid_encode_backward")
+
+    def grad_total_variation(inputs, emb, grad, offsets, weight, B, D, C, Lv, S_, H, gridtype, align_corners):
+        off = _offsets_host(offsets)
+        _ck(L.gfpp_grad_total_variation(_P(inputs, torch.float32), _P(emb, torch.float32), _P(grad, torch.float32), off.ctypes.data_as(ctypes.c_void_p),
+                                        cf(weight), B, D, C, Lv, cf(S_), H, gridtype, int(align_corners), S()), "grad_total_variation")
+
+    ge.grid_encode_backward = grid_encode_backward
+    ge.grad_total_variation = grad_total_variation
 
     sh = types.ModuleType("_shencoder")
 

@@ -32,6 +32,25 @@ cudaError_t launch_pack_octs_i16(const GridMeta &, const float *, void *, uint32
 // tc_pack.cu
 cudaError_t launch_pack_tc_tile(const float *, int, int, int, int, int, int, int, int, unsigned char *, unsigned char *, cudaStream_t);
 cudaError_t launch_tc_selftest(const float *, int, const unsigned char *, const unsigned char *, int, int, int, int, float *, cudaStream_t);
+// train_kernels.cu
+size_t march_train_scratch_bytes(uint32_t N);
+cudaError_t launch_march_rays_train(const MarchConst &, const float *, const float *, const float *, const float *, const float *, uint32_t,
+                                    uint32_t, uint32_t, float *, float *, float *, int *, int *, int *, int *, cudaStream_t);
+cudaError_t launch_march_rays_train_backward(const float *, const float *, const int *, const float *, uint32_t, uint32_t, float *, float *,
+                                             cudaStream_t);
+cudaError_t launch_composite_train_forward(const float *, const float *, const float *, const float *, const int *, uint32_t, uint32_t, float,
+                                           float *, float *, float *, float *, cudaStream_t);
+cudaError_t launch_composite_train_backward(const float *, const float *, const float *, const float *, const float *, const float *,
+                                            const float *, const int *, const float *, const float *, const float *, uint32_t, uint32_t, float,
+                                            float *, float *, float *, cudaStream_t);
+cudaError_t launch_grid_encode_dydx(const GridMeta &, const float *, const float *, float *, float *, uint32_t, cudaStream_t);
+cudaError_t launch_grid_backward(const GridMeta &, const float *, const float *, float *, const float *, float *, uint32_t, int *, cudaStream_t);
+cudaError_t launch_grad_tv(const GridMeta &, const float *, const float *, float *, float, uint32_t, cudaStream_t);
+cudaError_t launch_packbits(const float *, uint32_t, float, uint8_t *, cudaStream_t);
+cudaError_t launch_morton3D(const int *, uint32_t, int *, cudaStream_t);
+cudaError_t launch_morton3D_invert(const int *, uint32_t, int *, cudaStream_t);
+cudaError_t launch_morton3D_dilation(const float *, uint32_t, uint32_t, float *, cudaStream_t);
+cudaError_t launch_sph_from_ray(const float *, const float *, float, uint32_t, float *, cudaStream_t);
 }  // namespace gfpp
 
 using namespace gfpp;
@@ -966,6 +985,143 @@ int gfpp_torso_sr_composite(const gfpp_torso_sr_model *model, const gfpp_torso_s
         k_copy_ints<<<(fr->n_frames + 127) / 128, 128, 0, st>>>(t.P_count, (int)fr->n_frames, torso_pixels);
         CK(cudaGetLastError());
     }
+    return GFPP_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ (D) training-side ops (train_kernels.cu)
+extern "C" {
+
+size_t gfpp_march_rays_train_scratch_bytes(uint32_t N) { return march_train_scratch_bytes(N); }
+
+int gfpp_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma, uint32_t max_steps,
+                          uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears, const float *fars, float *xyzs, float *dirs,
+                          float *deltas, int32_t *rays, int32_t *counter, const float *noises, void *scratch, size_t scratch_bytes,
+                          void *stream) {
+    if (!rays_o || !rays_d || !grid || !nears || !fars || !xyzs || !dirs || !deltas || !rays || !counter || !noises || !scratch)
+        return fail(GFPP_ERR_INVALID, "march_rays_train: null pointer%s");
+    if (C < 1 || C > 8 || H < 1 || H > 1024 || max_steps < 1) return fail(GFPP_ERR_INVALID, "march_rays_train: bad C/H/max_steps%s");
+    if (scratch_bytes < march_train_scratch_bytes(N)) return fail(GFPP_ERR_WORKSPACE, "march_rays_train: scratch too small%s");
+    if (N > (1u << 24)) return fail(GFPP_ERR_UNSUPPORTED, "march_rays_train: N <= 2^24 rays per call%s");
+    MarchConst mc;
+    march_const_init(mc, bound, dt_gamma, max_steps, C, H, grid);
+    g_launches = 0;
+    int nl = 0;
+    CKN(launch_march_rays_train(mc, rays_o, rays_d, nears, fars, noises, N, M, max_steps, xyzs, dirs, deltas, (int *)rays, (int *)counter,
+                                (int *)scratch, &nl, (cudaStream_t)stream));
+    g_launches = nl;
+    return GFPP_OK;
+}
+
+int gfpp_march_rays_train_backward(const float *grad_xyzs, const float *grad_dirs, const int32_t *rays, const float *deltas, uint32_t N,
+                                   uint32_t M, float *grad_rays_o, float *grad_rays_d, void *stream) {
+    if (!grad_xyzs || !grad_dirs || !rays || !deltas || !grad_rays_o || !grad_rays_d) return fail(GFPP_ERR_INVALID, "march_rays_train_backward: null pointer%s");
+    g_launches = 0;
+    CK(launch_march_rays_train_backward(grad_xyzs, grad_dirs, (const int *)rays, deltas, N, M, grad_rays_o, grad_rays_d, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *ambient, const float *deltas, const int32_t *rays,
+                                      uint32_t M, uint32_t N, float T_thresh, float *weights_sum, float *ambient_sum, float *depth,
+                                      float *image, void *stream) {
+    if (!sigmas || !rgbs || !ambient || !deltas || !rays || !weights_sum || !ambient_sum || !depth || !image)
+        return fail(GFPP_ERR_INVALID, "composite_rays_train_forward: null pointer%s");
+    g_launches = 0;
+    CK(launch_composite_train_forward(sigmas, rgbs, ambient, deltas, (const int *)rays, M, N, T_thresh, weights_sum, ambient_sum, depth, image,
+                                      (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_composite_rays_train_backward(const float *grad_weights_sum, const float *grad_ambient_sum, const float *grad_image,
+                                       const float *sigmas, const float *rgbs, const float *ambient, const float *deltas, const int32_t *rays,
+                                       const float *weights_sum, const float *ambient_sum, const float *image, uint32_t M, uint32_t N,
+                                       float T_thresh, float *grad_sigmas, float *grad_rgbs, float *grad_ambient, void *stream) {
+    if (!grad_weights_sum || !grad_ambient_sum || !grad_image || !sigmas || !rgbs || !ambient || !deltas || !rays || !weights_sum || !ambient_sum ||
+        !image || !grad_sigmas || !grad_rgbs || !grad_ambient)
+        return fail(GFPP_ERR_INVALID, "composite_rays_train_backward: null pointer%s");
+    g_launches = 0;
+    CK(launch_composite_train_backward(grad_weights_sum, grad_ambient_sum, grad_image, sigmas, rgbs, ambient, deltas, (const int *)rays,
+                                       weights_sum, ambient_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs, grad_ambient, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_grid_encode_forward_dydx(const float *inputs, const float *embeddings, const int32_t *offsets_host, float *outputs, uint32_t B,
+                                  uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, float *dy_dx, uint32_t gridtype, int align_corners,
+                                  uint32_t interp, void *stream) {
+    if (!inputs || !embeddings || !offsets_host || !outputs || !dy_dx) return fail(GFPP_ERR_INVALID, "grid_encode_forward_dydx: null pointer%s");
+    if (C != 2) return fail(GFPP_ERR_UNSUPPORTED, "GridEncoding: this build supports C == 2 only%s");
+    GridMeta gm;
+    if (fill_grid_meta(gm, offsets_host, D, L, S, H, gridtype, align_corners, interp) != 0)
+        return fail(GFPP_ERR_UNSUPPORTED, "GridEncoding: D must be 2 or 3 and L <= 16%s");
+    g_launches = 0;
+    CK(launch_grid_encode_dydx(gm, inputs, embeddings, outputs, dy_dx, B, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_grid_encode_backward(const float *grad, const float *inputs, const float *embeddings, const int32_t *offsets_host,
+                              float *grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, const float *dy_dx,
+                              float *grad_inputs, uint32_t gridtype, int align_corners, uint32_t interp, void *stream) {
+    (void)embeddings;   // the reference passes the table too (gridencoder.h:13) but only uses its dtype
+    if (!grad || !inputs || !offsets_host || !grad_embeddings) return fail(GFPP_ERR_INVALID, "grid_encode_backward: null pointer%s");
+    if ((dy_dx == nullptr) != (grad_inputs == nullptr)) return fail(GFPP_ERR_INVALID, "grid_encode_backward: dy_dx and grad_inputs go together%s");
+    if (C != 2) return fail(GFPP_ERR_UNSUPPORTED, "GridEncoding: this build supports C == 2 only%s");
+    GridMeta gm;
+    if (fill_grid_meta(gm, offsets_host, D, L, S, H, gridtype, align_corners, interp) != 0)
+        return fail(GFPP_ERR_UNSUPPORTED, "GridEncoding: D must be 2 or 3 and L <= 16%s");
+    g_launches = 0;
+    int nl = 0;
+    CKN(launch_grid_backward(gm, grad, inputs, grad_embeddings, dy_dx, grad_inputs, B, &nl, (cudaStream_t)stream));
+    g_launches = nl;
+    return GFPP_OK;
+}
+
+int gfpp_grad_total_variation(const float *inputs, const float *embeddings, float *grad, const int32_t *offsets_host, float weight, uint32_t B,
+                              uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners, void *stream) {
+    if (!inputs || !embeddings || !grad || !offsets_host) return fail(GFPP_ERR_INVALID, "grad_total_variation: null pointer%s");
+    if (C != 2) return fail(GFPP_ERR_UNSUPPORTED, "GridEncoding: this build supports C == 2 only%s");
+    GridMeta gm;
+    if (fill_grid_meta(gm, offsets_host, D, L, S, H, gridtype, align_corners, 0) != 0)
+        return fail(GFPP_ERR_UNSUPPORTED, "GridEncoding: D must be 2 or 3 and L <= 16%s");
+    g_launches = 0;
+    CK(launch_grad_tv(gm, inputs, embeddings, grad, weight, B, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *bitfield, void *stream) {
+    if (!grid || !bitfield) return fail(GFPP_ERR_INVALID, "packbits: null pointer%s");
+    if (((uintptr_t)grid & 15u) != 0) return fail(GFPP_ERR_INVALID, "packbits: grid must be 16-byte aligned%s");
+    g_launches = 0;
+    CK(launch_packbits(grid, N, density_thresh, bitfield, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_morton3D(const int32_t *coords, uint32_t N, int32_t *indices, void *stream) {
+    if (!coords || !indices) return fail(GFPP_ERR_INVALID, "morton3D: null pointer%s");
+    g_launches = 0;
+    CK(launch_morton3D((const int *)coords, N, (int *)indices, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_morton3D_invert(const int32_t *indices, uint32_t N, int32_t *coords, void *stream) {
+    if (!coords || !indices) return fail(GFPP_ERR_INVALID, "morton3D_invert: null pointer%s");
+    g_launches = 0;
+    CK(launch_morton3D_invert((const int *)indices, N, (int *)coords, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_morton3D_dilation(const float *grid, uint32_t C, uint32_t H, float *grid_dilation, void *stream) {
+    if (!grid || !grid_dilation) return fail(GFPP_ERR_INVALID, "morton3D_dilation: null pointer%s");
+    if (C < 1 || C > 8 || H < 1 || H > 1024) return fail(GFPP_ERR_INVALID, "morton3D_dilation: bad C/H%s");
+    g_launches = 0;
+    CK(launch_morton3D_dilation(grid, C, H, grid_dilation, (cudaStream_t)stream));
+    return GFPP_OK;
+}
+
+int gfpp_sph_from_ray(const float *rays_o, const float *rays_d, float radius, uint32_t N, float *coords, void *stream) {
+    if (!rays_o || !rays_d || !coords) return fail(GFPP_ERR_INVALID, "sph_from_ray: null pointer%s");
+    g_launches = 0;
+    CK(launch_sph_from_ray(rays_o, rays_d, radius, N, coords, (cudaStream_t)stream));
     return GFPP_OK;
 }
 

@@ -27,6 +27,8 @@
  *
  *  (C) the SR checkpoints' extra stages: gfpp_sr_* (256 -> 512 super-resolution head) and
  *      gfpp_torso_sr_* (the torso field of radnerf_torso_sr.py), declared at the end of this file.
+ *
+ *  (D) the training-side native ops, mirroring the reference's pybind functions like (A).
  */
 #ifndef GFPP_H_
 #define GFPP_H_
@@ -306,6 +308,60 @@ GFPP_API size_t gfpp_torso_sr_workspace_bytes(uint32_t n_frames);
 GFPP_API int gfpp_torso_sr_composite(const gfpp_torso_sr_model *model, const gfpp_torso_sr_frames *frames, float *rgb_map,
                                      float *torso_alpha_map, float *torso_rgb_map, float *torso_deform, int32_t *torso_pixels,
                                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------ (D) training-side ops
+ *
+ * Mirror, argument for argument (+ stream; grid offsets as a host pointer, as in (A)), the training-side pybind functions of
+ * the reference's extensions, so that its own autograd wrappers (raymarching.py:184-344, grid.py:24-88) can bind them:
+ *   gfpp_march_rays_train                <- raymarching.h:14 (raymarching.cu:352-533)
+ *   gfpp_march_rays_train_backward       <- raymarching.h:15 (raymarching.cu:535-598)
+ *   gfpp_composite_rays_train_forward    <- raymarching.h:16 (raymarching.cu:603-700)
+ *   gfpp_composite_rays_train_backward   <- raymarching.h:17 (raymarching.cu:711-822)
+ *   gfpp_grid_encode_forward_dydx        <- gridencoder.h:12 with dy_dx given (gridencoder.cu:87-243)
+ *   gfpp_grid_encode_backward            <- gridencoder.h:13 (gridencoder.cu:246-368, 413-443)
+ *   gfpp_grad_total_variation            <- gridencoder.h:15 (gridencoder.cu:505-609)
+ *   gfpp_packbits / gfpp_morton3D / gfpp_morton3D_invert / gfpp_morton3D_dilation / gfpp_sph_from_ray
+ *                                        <- raymarching.h:8-12 (raymarching.cu:162-342; update_extra_state)
+ * fp32 only.  One deliberate difference: gfpp_march_rays_train is deterministic -- point offsets are an exclusive prefix sum of
+ * the per-ray sample counts in ray order (rays[n] = (n, offset, num_steps)) instead of the reference's atomicAdd arrival
+ * order; every consumer addresses samples through `rays`, so this is one of the layouts the reference itself can produce.
+ * It needs a small scratch buffer for the device-wide scan (query the size first).  `counter` keeps the reference's
+ * meaning: counter[0] += points, counter[1] += N. */
+GFPP_API size_t gfpp_march_rays_train_scratch_bytes(uint32_t N);
+GFPP_API int gfpp_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound, float dt_gamma,
+                                   uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *nears,
+                                   const float *fars, float *xyzs, float *dirs, float *deltas, int32_t *rays, int32_t *counter,
+                                   const float *noises, void *scratch, size_t scratch_bytes, void *stream);
+/* grad_rays_o / grad_rays_d [N,3] are accumulated into (+=), as in the reference */
+GFPP_API int gfpp_march_rays_train_backward(const float *grad_xyzs, const float *grad_dirs, const int32_t *rays, const float *deltas,
+                                            uint32_t N, uint32_t M, float *grad_rays_o, float *grad_rays_d, void *stream);
+GFPP_API int gfpp_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *ambient, const float *deltas,
+                                               const int32_t *rays, uint32_t M, uint32_t N, float T_thresh, float *weights_sum,
+                                               float *ambient_sum, float *depth, float *image, void *stream);
+/* grad_sigmas [M], grad_rgbs [M,3], grad_ambient [M] must be zero-initialised by the caller (raymarching.py:316-318) */
+GFPP_API int gfpp_composite_rays_train_backward(const float *grad_weights_sum, const float *grad_ambient_sum, const float *grad_image,
+                                                const float *sigmas, const float *rgbs, const float *ambient, const float *deltas,
+                                                const int32_t *rays, const float *weights_sum, const float *ambient_sum,
+                                                const float *image, uint32_t M, uint32_t N, float T_thresh, float *grad_sigmas,
+                                                float *grad_rgbs, float *grad_ambient, void *stream);
+/* outputs [L,B,C] as gfpp_grid_encode_forward, plus dy_dx [B, L, D, C] */
+GFPP_API int gfpp_grid_encode_forward_dydx(const float *inputs, const float *embeddings, const int32_t *offsets_host, float *outputs,
+                                           uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, float *dy_dx,
+                                           uint32_t gridtype, int align_corners, uint32_t interp, void *stream);
+/* grad [L,B,C]; grad_embeddings (zero-initialised by the caller, grid.py:76) is accumulated into with vector reductions;
+ * dy_dx / grad_inputs [B,D]: both or neither */
+GFPP_API int gfpp_grid_encode_backward(const float *grad, const float *inputs, const float *embeddings, const int32_t *offsets_host,
+                                       float *grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                       const float *dy_dx, float *grad_inputs, uint32_t gridtype, int align_corners, uint32_t interp,
+                                       void *stream);
+GFPP_API int gfpp_grad_total_variation(const float *inputs, const float *embeddings, float *grad, const int32_t *offsets_host,
+                                       float weight, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                       uint32_t gridtype, int align_corners, void *stream);
+GFPP_API int gfpp_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *bitfield, void *stream);
+GFPP_API int gfpp_morton3D(const int32_t *coords, uint32_t N, int32_t *indices, void *stream);
+GFPP_API int gfpp_morton3D_invert(const int32_t *indices, uint32_t N, int32_t *coords, void *stream);
+GFPP_API int gfpp_morton3D_dilation(const float *grid, uint32_t C, uint32_t H, float *grid_dilation, void *stream);
+GFPP_API int gfpp_sph_from_ray(const float *rays_o, const float *rays_d, float radius, uint32_t N, float *coords, void *stream);
 
 #ifdef __cplusplus
 }

@@ -179,3 +179,113 @@ def linear(x, W, relu=False):
     y = torch.empty(M, N, dtype=torch.float32)
     lib().orc_linear(_f(x), _f(W), _f(y), u32(M), u32(K), u32(N), ctypes.c_int(int(relu)))
     return y
+
+
+# ---------------------------------------------------------------- training side
+def march_rays_train(rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, M=None, noises=None, dt_gamma=0.0, max_steps=1024,
+                     counter=None):
+    """raymarching.py:184-260 at wrapper level, without the mean_count / align logic: returns (xyzs [M,3], dirs [M,3],
+    deltas [M,2], rays [N,3], counter [2]); point offsets in ray order (the checker's layout, see native_ops.c)."""
+    rays_o = rays_o.float().contiguous().view(-1, 3)
+    rays_d = rays_d.float().contiguous().view(-1, 3)
+    N = rays_o.shape[0]
+    M = N * max_steps if M is None else M
+    xyzs = torch.zeros(M, 3); dirs = torch.zeros(M, 3); deltas = torch.zeros(M, 2)
+    rays = torch.empty(N, 3, dtype=torch.int32)
+    counter = torch.zeros(2, dtype=torch.int32) if counter is None else counter
+    noises = torch.zeros(N) if noises is None else noises.float().contiguous()
+    lib().orc_march_rays_train(_f(rays_o), _f(rays_d), _b(density_bitfield), ctypes.c_float(bound), ctypes.c_float(dt_gamma), u32(max_steps),
+                               u32(N), u32(C), u32(H), u32(M), _f(nears), _f(fars), _f(xyzs), _f(dirs), _f(deltas), _i(rays), _i(counter),
+                               _f(noises))
+    return xyzs, dirs, deltas, rays, counter
+
+
+def march_rays_train_backward(grad_xyzs, grad_dirs, rays, deltas):
+    N, M = rays.shape[0], grad_xyzs.shape[0]
+    go, gd = torch.zeros(N, 3), torch.zeros(N, 3)
+    lib().orc_march_rays_train_backward(_f(grad_xyzs.float().contiguous()), _f(grad_dirs.float().contiguous()), _i(rays), _f(deltas), u32(N), u32(M),
+                                        _f(go), _f(gd))
+    return go, gd
+
+
+def composite_rays_train_forward(sigmas, rgbs, ambient, deltas, rays, T_thresh=1e-4):
+    M, N = sigmas.shape[0], rays.shape[0]
+    ws, asum, depth, image = torch.empty(N), torch.empty(N), torch.empty(N), torch.empty(N, 3)
+    lib().orc_composite_rays_train_forward(_f(sigmas.float().contiguous()), _f(rgbs.float().contiguous()), _f(ambient.float().contiguous()), _f(deltas),
+                                           _i(rays), u32(M), u32(N), ctypes.c_float(T_thresh), _f(ws), _f(asum), _f(depth), _f(image))
+    return ws, asum, depth, image
+
+
+def composite_rays_train_backward(grad_ws, grad_asum, grad_image, sigmas, rgbs, ambient, deltas, rays, ws, asum, image, T_thresh=1e-4):
+    M, N = sigmas.shape[0], rays.shape[0]
+    gs, gr, ga = torch.zeros(M), torch.zeros(M, 3), torch.zeros(M)
+    lib().orc_composite_rays_train_backward(_f(grad_ws.float().contiguous()), _f(grad_asum.float().contiguous()), _f(grad_image.float().contiguous()),
+                                            _f(sigmas.float().contiguous()), _f(rgbs.float().contiguous()), _f(ambient.float().contiguous()), _f(deltas),
+                                            _i(rays), _f(ws), _f(asum), _f(image), u32(M), u32(N), ctypes.c_float(T_thresh), _f(gs), _f(gr), _f(ga))
+    return gs, gr, ga
+
+
+def grid_encode_dydx(inputs01, embeddings, offsets, per_level_scale, base_resolution, gridtype_id=1, align_corners=False, interp_id=0):
+    """dy_dx [B, L, D, C] of the forward (gridencoder.cu:198-243)."""
+    inputs01 = inputs01.float().contiguous()
+    B, D = inputs01.shape
+    L, C = offsets.shape[0] - 1, embeddings.shape[1]
+    out = torch.empty(B, L, D, C)
+    rc = lib().orc_grid_encode_dydx(_f(inputs01), _f(embeddings.float().contiguous()), _i(offsets.int().contiguous()), _f(out), u32(B), u32(D), u32(C),
+                                    u32(L), ctypes.c_float(float(np.log2(per_level_scale))), u32(base_resolution), u32(gridtype_id),
+                                    ctypes.c_int(int(align_corners)), u32(interp_id))
+    assert rc == 0
+    return out
+
+
+def grid_encode_backward(grad_BLC, inputs01, embeddings, offsets, per_level_scale, base_resolution, gridtype_id=1, align_corners=False, interp_id=0,
+                         dy_dx=None):
+    """grad_BLC [B, L*C] (the autograd layout, grid.py:72-74) -> (grad_embeddings [sum,C], grad_inputs [B,D] or None)."""
+    inputs01 = inputs01.float().contiguous()
+    B, D = inputs01.shape
+    L, C = offsets.shape[0] - 1, embeddings.shape[1]
+    grad = grad_BLC.float().view(B, L, C).permute(1, 0, 2).contiguous()
+    ge = torch.zeros_like(embeddings, dtype=torch.float32)
+    gi = torch.zeros(B, D) if dy_dx is not None else None
+    rc = lib().orc_grid_encode_backward(_f(grad), _f(inputs01), _i(offsets.int().contiguous()), _f(ge), u32(B), u32(D), u32(C), u32(L),
+                                        ctypes.c_float(float(np.log2(per_level_scale))), u32(base_resolution),
+                                        _f(dy_dx.float().contiguous()) if dy_dx is not None else None, _f(gi) if gi is not None else None,
+                                        u32(gridtype_id), ctypes.c_int(int(align_corners)), u32(interp_id))
+    assert rc == 0
+    return ge, gi
+
+
+def grad_total_variation(inputs01, embeddings, offsets, weight, per_level_scale, base_resolution, gridtype_id=1, align_corners=False, grad=None):
+    inputs01 = inputs01.float().contiguous()
+    B, D = inputs01.shape
+    L, C = offsets.shape[0] - 1, embeddings.shape[1]
+    grad = torch.zeros_like(embeddings, dtype=torch.float32) if grad is None else grad
+    rc = lib().orc_grad_total_variation(_f(inputs01), _f(embeddings.float().contiguous()), _f(grad), _i(offsets.int().contiguous()), ctypes.c_float(weight),
+                                        u32(B), u32(D), u32(C), u32(L), ctypes.c_float(float(np.log2(per_level_scale))), u32(base_resolution),
+                                        u32(gridtype_id), ctypes.c_int(int(align_corners)))
+    assert rc == 0
+    return grad
+
+
+def morton3D_invert(indices):
+    indices = indices.int().contiguous().view(-1)
+    out = torch.empty(indices.shape[0], 3, dtype=torch.int32)
+    lib().orc_morton3D_invert(_i(indices), u32(indices.shape[0]), _i(out))
+    return out
+
+
+def morton3D_dilation(grid):
+    grid = grid.float().contiguous()
+    C, H3 = grid.shape
+    H = int(round(H3 ** (1.0 / 3.0)))
+    out = torch.empty_like(grid)
+    lib().orc_morton3D_dilation(_f(grid), u32(C), u32(H), _f(out))
+    return out
+
+
+def sph_from_ray(rays_o, rays_d, radius):
+    rays_o = rays_o.float().contiguous().view(-1, 3)
+    rays_d = rays_d.float().contiguous().view(-1, 3)
+    out = torch.empty(rays_o.shape[0], 2)
+    lib().orc_sph_from_ray(_f(rays_o), _f(rays_d), ctypes.c_float(radius), u32(rays_o.shape[0]), _f(out))
+    return out
