@@ -51,19 +51,24 @@ def _upsample_skip(img):
 
 
 @torch.no_grad()
-def emulate(fw, rgb_flat, R, noise=(None, None, None, None), fp16=True, clamp=False):
+def emulate(fw, rgb_flat, R, noise=(None, None, None, None), fp16=True, clamp=False, intermediates=None):
     """fw: folded_weights() dict (CPU tensors); rgb_flat [F, R*R, 3]; noise[i]: None or [res,res] / [F,res,res] planes already
-    multiplied by the layer's strength.  Returns [F,3,2R,2R]."""
+    multiplied by the layer's strength.  Returns [F,3,2R,2R].  `intermediates`: optional dict that receives the tensors the
+    kernels keep in their workspace (x0a, x0b: [F,R,R,128]; img0 [F,R,R,3]; x1a [F,2R,2R,64]) for layer-by-layer diagnosis."""
     x = rgb_flat.reshape(-1, R, R, 3).float()
     Fn = x.shape[0]
     h = _im2col(x) @ fw["conv_in_w"]                                        # fp32 FFMA layer, [F,R,R,128]
     h = _r16(_act(h, noise[0], fw["bias"][0]), fp16)                        # stored as fp16 NHWC
+    x0a = h
     a = _act(_im2col(h) @ _r16(fw["conv0_w"], fp16).t(), noise[1], fw["bias"][1])
     img0 = x + (a @ fw["rgb_w"][0].t() + fw["rgb_b"][0]).clamp(-256.0, 256.0)   # toRGB on the unrounded activations
     h = _r16(a, fp16)
     u = _im2col(h) @ _r16(fw["up_w"], fp16).t()                             # [F,R,R,256], column (py*2+px)*64 + co
     u = u.reshape(Fn, R, R, 2, 2, 64).permute(0, 1, 3, 2, 4, 5).reshape(Fn, 2 * R, 2 * R, 64)
+    x0b = h
     h = _r16(_act(u, noise[2], fw["bias"][2]), fp16)
+    if intermediates is not None:
+        intermediates.update(x0a=x0a, x0b=x0b, img0=img0, x1a=h)
     a = _act(_im2col(h) @ _r16(fw["conv1_w"], fp16).t(), noise[3], fw["bias"][3])
     img = _upsample_skip(img0) + (a @ fw["rgb_w"][1].t() + fw["rgb_b"][1]).clamp(-256.0, 256.0)
     if clamp:

@@ -48,13 +48,25 @@ def test_native_sr_head_matches_emulation_and_fp32(mode):
             gen = torch.Generator().manual_seed(5)
             nz = [torch.randn(3, l.resolution, l.resolution, generator=gen) * 0.05 for l in lay]
             ref = None
-        emu = emulate(net.folded_weights(), flat, 256, nz, fp16=True)
+        inter = {}
+        emu = emulate(net.folded_weights(), flat, 256, nz, fp16=True, intermediates=inter)
     net = net.cuda()
     net.backend = "native"
     got = net.forward_native(flat.cuda(), noise_mode="none" if mode == "none" else "const",
                              noise_planes=None if mode != "planes" else [p.cuda() for p in nz], frames_per_call=2)
     torch.cuda.synchronize()
     got = got.cpu()
+    # layer-by-layer diagnosis from the kernels' workspace (last chunk of frames: frames_per_call=2 -> frame 2 only)
+    ws, R, n_last = net.__dict__["_native"]["ws"], 256, 1
+    px = n_last * R * R
+    off, parts = 0, {}
+    for name, numel, dt in (("x0a", px * 128, torch.float16), ("x0b", px * 128, torch.float16), ("img0", px * 3, torch.float32), ("x1a", px * 4 * 64, torch.float16)):
+        nbytes = numel * (2 if dt == torch.float16 else 4)
+        parts[name] = ws[off:off + nbytes].view(dt).float().cpu()
+        off += (nbytes + 255) // 256 * 256
+    for name, t in parts.items():
+        ref_t = inter[name][2:3].reshape(-1)
+        print(f"[{mode}] workspace {name}: max |kernel - emulation| = {(t - ref_t).abs().max().item():.3e} (scale {ref_t.abs().max().item():.2f})")
     assert torch.isfinite(got).all()
     e_model = (got - emu).abs().max().item()
     print(f"[{mode}] |native - fp16 data-flow emulation| = {e_model:.3e}")

@@ -157,10 +157,11 @@ def test_grid_encode_autograd_and_tv_vs_checker(oracle_ops, D, gridtype, interp)
     e_y, e_t, e_x = (y.detach().cpu() - y_ref).abs().max().item(), (t_.grad.cpu() - ge_ref).abs().max().item(), (x_.grad.cpu() - gi_ref).abs().max().item()
     print(f"D={D} gridtype={gridtype} interp={interp}: forward {e_y:.2e}, table grad {e_t:.2e} (max {ge_ref.abs().max().item():.2e}), input grad {e_x:.2e} (max {gi_ref.abs().max().item():.2e})")
     assert e_y < 2e-6 and e_t < 2e-5 * max(1.0, ge_ref.abs().max().item()) and e_x < 1e-4 * max(1.0, gi_ref.abs().max().item())
-    tv_ref = oracle_ops.grad_total_variation(x, table, offsets, 0.5, lay.per_level_scale, 16, gridtype, False)
+    xb = x * 2 - 1                                     # the wrapper maps [-bound, bound] back to [0,1] (grid.py:180): feed both the same numbers
+    tv_ref = oracle_ops.grad_total_variation((xb + 1) / 2, table, offsets, 0.5, lay.per_level_scale, 16, gridtype, False)
     t2 = table.cuda().requires_grad_()
     t2.grad = torch.zeros_like(t2)
-    train_ops.grad_total_variation(t2, offsets.cuda(), lay.per_level_scale, 16, D, weight=0.5, inputs=x.cuda() * 2 - 1, bound=1, gridtype=gridtype)
+    train_ops.grad_total_variation(t2, offsets.cuda(), lay.per_level_scale, 16, D, weight=0.5, inputs=xb.cuda(), bound=1, gridtype=gridtype)
     torch.cuda.synchronize()
     e_tv = (t2.grad.cpu() - tv_ref).abs().max().item()
     print(f"TV grad {e_tv:.2e} (max {tv_ref.abs().max().item():.2e})")
@@ -249,17 +250,29 @@ def test_training_ops_vs_the_reference_kernels(oracle_ops):
     dy_o = oracle_ops.grid_encode_dydx(x, table, offsets, lay.per_level_scale, 16, 1, False, 0)
     ge_o, gi_o = oracle_ops.grid_encode_backward(G, x, table, offsets, lay.per_level_scale, 16, 1, False, 0, dy_dx=dy_o)
     torch.cuda.synchronize()
-    sc_t, sc_x = max(1.0, ge_o.abs().max().item()), max(1.0, gi_o.abs().max().item())
-    errs = {"dy_dx ref-checker": (dy_r.cpu().view(B, 16, 3, 2) - dy_o).abs().max().item() / max(1.0, dy_o.abs().max().item()),
-            "dy_dx ours-ref": (dy_g - dy_r).abs().max().item() / max(1.0, dy_o.abs().max().item()),
-            "table grad ref-checker": (ge_r.cpu() - ge_o).abs().max().item() / sc_t, "table grad ours-ref": (ge_g - ge_r).abs().max().item() / sc_t,
-            "input grad ref-checker": (gi_r.cpu() - gi_o).abs().max().item() / sc_x, "input grad ours-ref": (gi_g - gi_r).abs().max().item() / sc_x}
+    # The reference derives every level scale with the DEVICE exp2f (gridencoder.cu:137, <= 2 ulp), the checker and libgfpp with
+    # the host libm (tests/test_gpu_ref_pin.py): a sample within ~1e-4 cells of a cell face then sits in the neighbouring cell.
+    # Table gradients are continuous across that face; dy_dx (a per-cell slope), the input gradient built from it and the TV term
+    # (added to the cell's own entry) are not -- for those the disagreeing entries are COUNTED and bounded, the rest held to 1e-4.
     tv_r, tv_g = torch.zeros_like(table).cuda(), torch.zeros_like(table).cuda()
     ref_ge.grad_total_variation(x.cuda(), table.cuda(), tv_r, offsets.cuda(), 0.5, B, 3, 2, 16, S, 16, 1, False)
     ours["_gridencoder"].grad_total_variation(x.cuda(), table.cuda(), tv_g, offsets.cuda(), 0.5, B, 3, 2, 16, S, 16, 1, False)
     tv_o = oracle_ops.grad_total_variation(x, table, offsets, 0.5, lay.per_level_scale, 16, 1, False)
     torch.cuda.synchronize()
-    errs["tv ref-checker"] = (tv_r.cpu() - tv_o).abs().max().item() / max(1.0, tv_o.abs().max().item())
-    errs["tv ours-ref"] = (tv_g - tv_r).abs().max().item() / max(1.0, tv_o.abs().max().item())
-    print("grid encoder, relative to the largest entry: " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
-    assert all(v <= 1e-4 for v in errs.values()), errs
+
+    def cmp(name, a, b, scale, frac_allowed):
+        e = (a.cpu().reshape(-1) - b.cpu().reshape(-1)).abs() / scale
+        frac = (e > 1e-4).float().mean().item()
+        print(f"  {name}: max {e.max().item():.2e}, median {e.median().item():.2e}, entries over 1e-4: {frac:.2e} (allowed {frac_allowed:.0e})")
+        assert frac <= frac_allowed and e.median().item() <= 1e-5, name
+
+    print("grid encoder (errors relative to the largest entry):")
+    s_dy, s_t, s_x, s_tv = max(1.0, dy_o.abs().max().item()), max(1.0, ge_o.abs().max().item()), max(1.0, gi_o.abs().max().item()), max(1e-3, tv_o.abs().max().item())
+    cmp("dy_dx        reference vs checker", dy_r.view(B, 16, 3, 2), dy_o, s_dy, 2e-3)
+    cmp("dy_dx        libgfpp vs checker  ", dy_g.view(B, 16, 3, 2), dy_o, s_dy, 0.0)
+    cmp("table grad   reference vs checker", ge_r, ge_o, s_t, 1e-4)
+    cmp("table grad   libgfpp vs checker  ", ge_g, ge_o, s_t, 0.0)
+    cmp("input grad   reference vs checker", gi_r, gi_o, s_x, 2e-2)
+    cmp("input grad   libgfpp vs checker  ", gi_g, gi_o, s_x, 0.0)
+    cmp("TV grad      reference vs checker", tv_r, tv_o, s_tv, 1e-3)
+    cmp("TV grad      libgfpp vs checker  ", tv_g, tv_o, s_tv, 0.0)
