@@ -37,14 +37,16 @@ _OFFSETS_HOST = {}
 
 
 def _offsets_host(offsets):
-    """Host copy of a grid's level offsets, cached by (data_ptr, numel, version): no D2H sync per encoder call."""
+    """Host copy of a grid's level offsets, cached per offsets TENSOR: no D2H sync per encoder call.  The cache entry holds a
+    reference to the tensor, so its device address cannot be handed to another tensor while the entry lives (a cache keyed by
+    data_ptr alone returned a previous grid's offsets when a freed buffer's address was reused -- found on the B200)."""
     key = (offsets.data_ptr(), offsets.numel(), int(offsets._version))
-    off = _OFFSETS_HOST.get(key)
-    if off is None:
+    hit = _OFFSETS_HOST.get(key)
+    if hit is None or hit[0] is not offsets:
         if len(_OFFSETS_HOST) > 64:
             _OFFSETS_HOST.clear()
-        off = _OFFSETS_HOST[key] = np.ascontiguousarray(offsets.detach().cpu().numpy().astype(np.int32))
-    return off
+        hit = _OFFSETS_HOST[key] = (offsets, np.ascontiguousarray(offsets.detach().cpu().numpy().astype(np.int32)))
+    return hit[1]
 
 
 def _ck(rc, what):

@@ -538,7 +538,7 @@ class RADNeRFwithSR(RADNeRF):
         T = rgb.shape[0]
         out = torch.empty(T, 3, 2 * R, 2 * R, device=rgb.device, dtype=torch.float32)
         with torch.autocast(rgb.device.type, enabled=False):
-            if self.sr_net.backend == "native":
+            if rgb.is_cuda and self.sr_net.backend == "native":
                 # libgfpp's SR kernels read the renderer's [T,N,3] frames as they are and clamp in their last epilogue
                 self.sr_net.forward_native(rgb, noise_mode=sr_noise_mode, clamp=True, out=out, frames_per_call=sr_frames_per_call)
             else:
@@ -591,8 +591,8 @@ class RADNeRFTorsowithSR(RADNeRF):
     has_torso = False            # what gets packed for libgfpp is the head field only
     forwards_eye_area = True     # radnerf_torso_sr.py:136
     sr_input_resolution = 256
-    torso_backend = "torch"      # FLIP-AFTER-GPU-VALIDATION -> "native": libgfpp's k_torso_sr (csrc/torso_sr_kernel.cu); "torch":
-                                 # the host-side field below over libgfpp's per-op encoder kernels (the first correct path)
+    torso_backend = "native"     # libgfpp's k_torso_sr (csrc/torso_sr_kernel.cu); "torch": the host-side field below over libgfpp's
+                                 # per-op encoder kernels (the first correct path, kept as the A/B reference of the kernel)
 
     def __init__(self, hparams):
         super().__init__(hparams)

@@ -147,7 +147,7 @@ class _Block(nn.Module):
 class Superresolution(nn.Module):
     """radnerf_sr.py:15-48.  forward(rgb [B,3,h,w] in [0,1]) -> [B,3,512,512] (not clamped; the caller clamps)."""
 
-    backend = "torch"    # FLIP-AFTER-GPU-VALIDATION -> "native".  CUDA tensors: libgfpp's sm_100a kernels; "torch": the fp32 convolutions below (always on CPU tensors)
+    backend = "native"   # CUDA tensors: libgfpp's sm_100a kernels; "torch": the fp32 convolutions below (always on CPU tensors)
 
     def __init__(self, channels=3, img_resolution=512, sr_antialias=True):
         super().__init__()

@@ -1,6 +1,9 @@
 """The SR head on libgfpp's own sm_100a kernels (csrc/sr_kernel.cu) against
-  (i)  oracle/sr_emulate.py -- the CPU emulation of the kernels' data flow with the same fp16 operand rounding: agreement to
-       ~1e-5 separates layout / descriptor / pipeline bugs from rounding;
+  (i)  oracle/sr_emulate.py -- the CPU emulation of the kernels' data flow with the same fp16 operand rounding.  The fp16
+       activations the kernels keep in their workspace must equal the emulation's up to ONE fp16 ulp on a small fraction of
+       elements (fp32 accumulation order decides a rounding tie differently now and then; first B200 run: max 9.77e-4 = 2^-10
+       at |x| in [1,2), everything else identical), and the final image to 1e-3 (measured 3.3e-4: the effect of those flips).
+       A layout / descriptor / pipeline bug is O(1) on both;
   (ii) the fp32 convolutions of `Superresolution.forward` (pinned to the REFERENCE's Superresolution by tests/golden/sr_head.npz)
        and that golden itself: the 1e-3 bar on the clamped image the drivers consume."""
 import json
@@ -13,7 +16,7 @@ import torch
 from genefaceplusplus_b200 import scene as scn
 from genefaceplusplus_b200.superres import Superresolution
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("GFPP_PENDING") != "1", reason="first GPU run pending (GFPP_PENDING=1)")]
+pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -66,11 +69,18 @@ def test_native_sr_head_matches_emulation_and_fp32(mode):
         off += (nbytes + 255) // 256 * 256
     for name, t in parts.items():
         ref_t = inter[name][2:3].reshape(-1)
-        print(f"[{mode}] workspace {name}: max |kernel - emulation| = {(t - ref_t).abs().max().item():.3e} (scale {ref_t.abs().max().item():.2f})")
+        d = (t - ref_t).abs()
+        ulp = torch.maximum(ref_t.abs(), torch.tensor(2.0 ** -14)).log2().floor().exp2() * 2.0 ** -10      # fp16 spacing at the reference value
+        off = (d > 0).float().mean().item()
+        print(f"[{mode}] workspace {name}: max |kernel - emulation| = {d.max().item():.3e} (scale {ref_t.abs().max().item():.2f}), elements that differ: {off:.2e}")
+        if name == "img0":
+            assert d.max().item() <= 2e-4, name                      # fp32 toRGB + skip on (flipped-by-an-ulp) activations
+        else:
+            assert (d <= 1.001 * ulp).all() and off <= 0.02, name   # identical up to one fp16 ulp on a few elements
     assert torch.isfinite(got).all()
     e_model = (got - emu).abs().max().item()
     print(f"[{mode}] |native - fp16 data-flow emulation| = {e_model:.3e}")
-    assert e_model <= 1e-4, "layout / descriptor / pipeline error (not a rounding effect)"
+    assert e_model <= 1e-3, "layout / descriptor / pipeline error (not a rounding effect)"
     if ref is not None:
         e32 = (got.clamp(0, 1) - ref.clamp(0, 1)).abs().max().item()
         psnr = 10 * np.log10(1.0 / max((got.clamp(0, 1) - ref.clamp(0, 1)).square().mean().item(), 1e-20))
@@ -129,7 +139,9 @@ def _render(m, hp, sc, meta, t, **extra):
 @pytest.mark.parametrize("head_aware", [True, False])
 def test_torso_sr_field_native_matches_the_host_path(head_aware):
     """k_torso_sr (libgfpp) against the host-side torch field over the per-op encoder kernels -- itself pinned to the reference's
-    render() golden (tests/test_gpu_sr.py) -- on the same head image: fp32 both, so 1e-5 on every map."""
+    render() golden (tests/test_gpu_sr.py) -- on the same head image: fp32 both, so 2e-5 on every 256x256 map (first B200 run:
+    <= 1.0e-6).  `sr_rgb_map` goes through the host-side cuDNN convolutions here (TF32): two runs on inputs 5e-7 apart differ by
+    ~4e-4 there, so it only gets the 1e-3 bar."""
     m, hp, sc, z, meta = _torso_sr(head_aware)
     m.sr_net.backend = "torch"
     t = meta["frame"]
@@ -141,7 +153,7 @@ def test_torso_sr_field_native_matches_the_host_path(head_aware):
     for k in ("rgb_map", "torso_rgb_map", "torso_alpha_map", "deform", "sr_rgb_map"):
         e = (got[k].float() - ref[k].float()).abs().max().item()
         print(f"head_aware={head_aware} {k}: |native - host| = {e:.3e}")
-        assert got[k].shape == ref[k].shape and e <= (2e-5 if k != "sr_rgb_map" else 2e-4), (k, e)
+        assert got[k].shape == ref[k].shape and e <= (2e-5 if k != "sr_rgb_map" else 1e-3), (k, e)
     if head_aware:   # the golden was made with torso_head_aware=True: the reference's own render()
         for k, (a, b, c, d) in meta["crops"].items():
             e = (got[k][0, :, a:b, c:d].float().cpu() - torch.from_numpy(z[f"{k}_crop"])).abs().max().item()

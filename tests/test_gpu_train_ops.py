@@ -13,7 +13,7 @@ import torch
 from genefaceplusplus_b200 import scene as scn
 from genefaceplusplus_b200.config import GridLayout
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("GFPP_PENDING") != "1", reason="first GPU run pending (GFPP_PENDING=1)")]
+pytestmark = pytest.mark.gpu
 REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
 
 

@@ -273,6 +273,7 @@ def test_torso_sr_model_host_path_matches_the_reference_golden(oracle_ops, monke
 
     monkeypatch.setattr(RADNeRFTorsowithSR, "_head", fake_head)
     m.encoders = oracle_ops
+    m.torso_backend = "torch"        # the host-side field (A/B reference of libgfpp's k_torso_sr, which needs the GPU)
     kw = {k: v for k, v in hp.items() if k not in ("max_steps", "dt_gamma", "bg_color")}
     out = m.render(fi["rays_o"], fi["rays_d"], cond, fi["bg_coords"], fi["poses"], index=t, dt_gamma=hp["dt_gamma"], bg_color=fi["bg_color"],
                    max_steps=16, T_thresh=sc.T_thresh, upscale_torso=True, lm68=lm68, eye_area_percent=eye, staged=False, **kw)
