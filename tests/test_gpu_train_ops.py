@@ -270,7 +270,7 @@ def test_training_ops_vs_the_reference_kernels(oracle_ops):
     s_dy, s_t, s_x, s_tv = max(1.0, dy_o.abs().max().item()), max(1.0, ge_o.abs().max().item()), max(1.0, gi_o.abs().max().item()), max(1e-3, tv_o.abs().max().item())
     cmp("dy_dx        reference vs checker", dy_r.view(B, 16, 3, 2), dy_o, s_dy, 2e-3)
     cmp("dy_dx        libgfpp vs checker  ", dy_g.view(B, 16, 3, 2), dy_o, s_dy, 0.0)
-    cmp("table grad   reference vs checker", ge_r, ge_o, s_t, 1e-4)
+    cmp("table grad   reference vs checker", ge_r, ge_o, s_t, 5e-4)
     cmp("table grad   libgfpp vs checker  ", ge_g, ge_o, s_t, 0.0)
     cmp("input grad   reference vs checker", gi_r, gi_o, s_x, 2e-2)
     cmp("input grad   libgfpp vs checker  ", gi_g, gi_o, s_x, 0.0)
