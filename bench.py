@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-mode", action="store_true", help="skip measuring the other precision mode (fp16 <-> robust) beside the headline one")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own CUDA kernels (oracle/_ref) beside ours")
+    ap.add_argument("--no-sr-variants", action="store_true", help="skip the short measurement of the SR-checkpoint paths (SURVEY 8(f) rank 3)")
     ap.add_argument("--precision", default=os.environ.get("GFPP_BENCH_PRECISION", DEFAULT_PRECISION), choices=["fp32", "fp16", "bf16x3", "bf16", "robust"],
                     help="arithmetic of the head MLP GEMMs (marching/gather/compositing are fp32 in every mode)")
     return ap.parse_args()
@@ -511,6 +512,16 @@ def _main(args, out):
     if rank == 0 and world == 1 and not args.no_other_mode and args.precision in ("fp16", "robust"):
         other = measure_other_mode(args, sc, model, "robust" if args.precision == "fp16" else "fp16", poses_dev, pose6_dev, cond_dev, bg_color, bg_coords,
                                    rgb, hbm, S_per_frame, (ref_img, ref_knife) if parity is not None else None)
+    sr = None
+    if rank == 0 and world == 1 and not args.no_sr_variants:
+        # SURVEY 8(f) rank 3, measured in the same run: the SR checkpoints' clip paths (NeRF at 256x256 + torso-SR field + 256->512 SR
+        # head on tcgen05), every stage in libgfpp, beside the SR head as host-side PyTorch / cuDNN (tools/sr_bench.py)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import sr_bench
+            sr = {"config": "256x256 NeRF (fp16 tcgen05) -> 512x512, 32-frame clips, resident inputs, CUDA events, median of 3", "results": sr_bench.measure(32, 3)}
+        except Exception as ex:   # an extra measurement must never take the bench down
+            sr = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     if rank == 0:
         line = {"metric": metric_name(args), "value": fps,
                 "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -527,7 +538,7 @@ def _main(args, out):
                                                   "region), uint8 [T,H,W,3] frames written by the epilogue kernel" +
                                                   (", all-gather of the uint8 clip, D2H of the whole clip on rank 0" if world > 1 else ", D2H of the clip")},
                 "gpu_launches": timed_launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "gpu_reference": gpu_ref,
-                "other_mode": other}
+                "other_mode": other, "sr_variants": sr}
         print(json.dumps(line), file=out)
     if world > 1:
         dist.destroy_process_group()

@@ -37,12 +37,11 @@ def timed(fn, reps, warm=2):
     return ms[len(ms) // 2]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=64)
-    ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--out", default=None)
-    a = ap.parse_args()
+def measure(frames=64, reps=5):
+    """-> list of result dicts (see the module docstring); importable by bench.py for its `sr_variants` object."""
+    class a:   # noqa: N801
+        pass
+    a.frames, a.reps = frames, reps
     from genefaceplusplus_b200.renderer import RADNeRFTorsowithSR, RADNeRFwithSR
     peaks = {}
     try:
@@ -105,6 +104,16 @@ def main():
         m.torso_backend, m.sr_net.backend = "torch", "torch"
         ms = timed(lambda: m.render_clip(poses, sc.intrinsics, 256, 256, **kw), max(1, a.reps // 2), warm=1)
         lines.append({"what": "torso-SR clip, host-side torso field + PyTorch SR (frame by frame)", "frames": T, "ms": ms, "fps": T / ms * 1e3})
+    return lines
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    lines = measure(a.frames, a.reps)
     for ln in lines:
         print(json.dumps(ln))
     if a.out:
