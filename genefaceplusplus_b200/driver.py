@@ -18,14 +18,14 @@ from .dist import to_uint8
 
 
 def cond_feat_from_windows(model, cond_wins, eye_area_percent=None):
-    """All frames' `cal_cond_feat` in one pass: cond_wins = list/stack of T windows [S,1,C] (what the driver passes per frame,
+    """All frames' `cal_cond_feat` in one pass: cond_wins = list/stack of T windows [S,cond_win_size,C] (what the driver passes per frame,
     genefacepp_infer.py:420-422) -> [T,64].  Equals calling model.cal_cond_feat window by window."""
     wins = torch.stack([w.reshape(w.shape[0], -1) for w in cond_wins]) if not torch.is_tensor(cond_wins) else cond_wins.reshape(cond_wins.shape[0], cond_wins.shape[1], -1)
     T, S, C = wins.shape
     dev = model.density_bitfield.device
     wins = wins.to(dev).float()
     with torch.autocast(dev.type, enabled=False):
-        feat = model.cond_prenet(wins.reshape(T * S, 1, C))
+        feat = model.cond_prenet(wins.reshape(T * S, model.cond_win_size, C // model.cond_win_size))
         if model.add_eye_blink_cond:
             eye = None
             if eye_area_percent is not None and model.forwards_eye_area:

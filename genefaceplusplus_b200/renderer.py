@@ -52,23 +52,37 @@ class _GridParams(nn.Module):
 
 
 class _AudioNet(nn.Module):
-    """cond_encoder.py:98-143 for win_size == 1 (all strides 1)."""
+    """cond_encoder.py:98-143: four Conv1d(k=3, padding=1) with window-size dependent strides that shrink the window to one
+    step, then two Linear layers.  Same parameter names; same supported sizes -- the reference's `win_size == [5, 8]` branch can
+    never be taken, so 5 and 8 raise ValueError there and here."""
+    STRIDES = {1: (1, 1, 1, 1), 2: (2, 1, 1, 1), 3: (2, 2, 1, 1), 4: (2, 2, 1, 1), 16: (2, 2, 2, 2)}
 
-    def __init__(self, dim_in, dim_aud):
+    def __init__(self, dim_in, dim_aud, win_size=1):
         super().__init__()
+        if win_size not in self.STRIDES:
+            raise ValueError("unsupported win_size")
+        self.win_size = win_size
+        st = self.STRIDES[win_size]
         self.encoder_conv = nn.Sequential(
-            nn.Conv1d(dim_in, 32, 3, 1, 1), nn.LeakyReLU(0.02, True), nn.Conv1d(32, 32, 3, 1, 1), nn.LeakyReLU(0.02, True),
-            nn.Conv1d(32, 64, 3, 1, 1), nn.LeakyReLU(0.02, True), nn.Conv1d(64, 64, 3, 1, 1), nn.LeakyReLU(0.02, True))
+            nn.Conv1d(dim_in, 32, 3, st[0], 1), nn.LeakyReLU(0.02, True), nn.Conv1d(32, 32, 3, st[1], 1), nn.LeakyReLU(0.02, True),
+            nn.Conv1d(32, 64, 3, st[2], 1), nn.LeakyReLU(0.02, True), nn.Conv1d(64, 64, 3, st[3], 1), nn.LeakyReLU(0.02, True))
         self.encoder_fc1 = nn.Sequential(nn.Linear(64, 64), nn.LeakyReLU(0.02, True), nn.Linear(64, dim_aud))
 
-    def forward(self, x):  # [b, t=1, c]
-        # Conv1d(k=3, padding=1) on a length-1 sequence only ever sees its centre tap: y = W[:, :, 1] x + b.  Written as
-        # plain fp32 matmuls (a handful of launches per clip) instead of per-sample im2col convolutions.
-        x = x.reshape(x.shape[0], -1)
+    def forward(self, x):  # [b, t=win_size, c]
+        if self.win_size == 1:
+            # Conv1d(k=3, padding=1) on a length-1 sequence only ever sees its centre tap: y = W[:, :, 1] x + b.  Written as
+            # plain fp32 matmuls (a handful of launches per clip) instead of per-sample im2col convolutions.
+            x = x.reshape(x.shape[0], -1)
+            for i in (0, 2, 4, 6):
+                conv = self.encoder_conv[i]
+                x = F.leaky_relu(F.linear(x, conv.weight[:, :, 1], conv.bias), 0.02)
+            return self.encoder_fc1(x)
+        # audio-window conditioning (deepspeech 16x29, esperanto): the strided stack as the reference runs it
+        y = x.permute(0, 2, 1)
         for i in (0, 2, 4, 6):
             conv = self.encoder_conv[i]
-            x = F.leaky_relu(F.linear(x, conv.weight[:, :, 1], conv.bias), 0.02)
-        return self.encoder_fc1(x)
+            y = F.leaky_relu(F.conv1d(y, conv.weight, conv.bias, stride=conv.stride, padding=1), 0.02)
+        return self.encoder_fc1(y.squeeze(-1))
 
 
 class _AudioAttNet(nn.Module):
@@ -139,9 +153,7 @@ class RADNeRF(nn.Module):
         self.cond_out_dim = hp["cond_out_dim"] // 2 * 2
         self.cond_win_size = hp["cond_win_size"]
         self.smo_win_size = hp["smo_win_size"]
-        if self.cond_win_size != 1:
-            raise NotImplementedError("cond_win_size != 1 (audio-window conditioning) is not on the May path")
-        self.cond_prenet = _AudioNet(self.cond_in_dim, self.cond_out_dim)
+        self.cond_prenet = _AudioNet(self.cond_in_dim, self.cond_out_dim, win_size=self.cond_win_size)
         # eye-blink conditioning of the SR-era configs (radnerf.py:40-47): same parameter names
         self.add_eye_blink_cond = bool(hp.get("add_eye_blink_cond", False))
         if self.add_eye_blink_cond:
@@ -215,7 +227,7 @@ class RADNeRF(nn.Module):
         return out
 
     def cal_cond_feat_clip(self, cond_seq, eye_area_percent=None):
-        """All frames at once: cond_seq [T,1,C] -> [T,64]; windows as get_audio_features(att_mode=2)
+        """All frames at once: cond_seq [T,cond_win_size,C] ([T,1,204] for the May configs) -> [T,64]; windows as get_audio_features(att_mode=2)
         (modules/radnerfs/utils.py:86-102: centred, zero-padded).  eye_area_percent: [T] (add_eye_blink_cond models)."""
         with torch.autocast("cuda", enabled=False):
             T = cond_seq.shape[0]
@@ -227,7 +239,7 @@ class RADNeRF(nn.Module):
             xp = torch.cat([pad, x, padr], 0)
             idx = torch.arange(T, device=x.device).unsqueeze(1) + torch.arange(S, device=x.device).unsqueeze(0)
             wins = xp[idx]                                                  # [T,S,C]
-            feat = self.cond_prenet(wins.reshape(T * S, 1, -1))
+            feat = self.cond_prenet(wins.reshape(T * S, self.cond_win_size, -1))
             if self.add_eye_blink_cond:
                 feat = self._add_blink(feat, eye_area_percent, T)
             feat = feat.view(T, S, -1)
@@ -437,8 +449,10 @@ class RADNeRF(nn.Module):
                force_all_rays=False, max_steps=1024, T_thresh=1e-4, cond_mask=None, eye_area_percent=None, **kwargs):
         if perturb:
             raise NotImplementedError("perturb=True is a training/GUI option; the inference driver passes False")
-        if cond_mask is not None:
-            raise NotImplementedError("cond_mask is unused by the May configs")
+        # cond_mask: accepted and ignored, exactly like the reference -- its forward() / density() take the argument and never read
+        # it (radnerf.py:108-141, 143-165); the only requirement renderer.py:371-372 puts on it is one entry per ray
+        if cond_mask is not None and torch.is_tensor(cond_mask) and cond_mask.shape[0] != rays_o.numel() // 3:
+            raise IndexError("cond_mask must have one entry per ray (renderer.py:372 indexes it with rays_alive)")
         prefix = rays_o.shape[:-1]
         if rays_o.numel() // 3 != int(np.prod(prefix)) or (len(prefix) > 1 and prefix[0] != 1):
             raise ValueError("render() assumes B == 1 (renderer.py:287)")

@@ -194,6 +194,41 @@ def test_sr_head_matches_the_reference_golden():
         assert (net(full, noise_mode="none") - net(full, noise_mode="const")).abs().max().item() > 1e-4
 
 
+def test_audio_window_prenet_matches_the_reference_golden():
+    """cond_win_size != 1 (audio-window conditioning: deepspeech 16x29, esperanto): `_AudioNet` against the REFERENCE's own AudioNet
+    outputs for every window size it supports (oracle/make_condwin_golden.py), same parameter names, and the same ValueError for the
+    sizes it rejects (its `win_size == [5, 8]` branch can never be taken)."""
+    import json
+    import os
+    from genefaceplusplus_b200.renderer import _AudioNet
+    from oracle.make_condwin_golden import condwin_state
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cond_win.npz"))
+    meta = json.loads(bytes(g["meta"]).decode())
+    for win, din in meta["cases"]:
+        net = _AudioNet(din, 64, win_size=win).eval()
+        net.load_state_dict(condwin_state(net.state_dict(), win), strict=True)
+        with torch.no_grad():
+            y = net(torch.from_numpy(g[f"w{win}_x"]))
+        assert (y - torch.from_numpy(g[f"w{win}_y"])).abs().max().item() < 2e-6, win
+    for win in meta["unsupported"]:
+        with pytest.raises(ValueError):
+            _AudioNet(29, 64, win_size=win)
+    # the model accepts the audio-window configs and batches them over a clip exactly like frame-by-frame cal_cond_feat
+    hp = may_hparams(cond_type="deepspeech", cond_win_size=16, smo_win_size=8)
+    m = RADNeRF(hp).eval()
+    assert m.cond_prenet.encoder_conv[0].stride == (2,) and m.cond_in_dim == 29
+    seq = scn.hashed_uniform(6 * 16 * 29, 31, 2.0).reshape(6, 16, 29)
+    with torch.no_grad():
+        clip = m.cal_cond_feat_clip(seq)
+        for t in (0, 3, 5):
+            win = torch.zeros(8, 16, 29)
+            for j in range(8):
+                i = t - 4 + j
+                if 0 <= i < 6:
+                    win[j] = seq[i]
+            assert (clip[t] - m.cal_cond_feat(win).reshape(-1)).abs().max().item() < 1e-5
+
+
 def test_sr_folded_weights_reproduce_the_fp32_head():
     """Host half of the native SR path (superres.folded_weights: modulation + demodulation folded, transposed stride-2
     convolution and its FIR merged into four 3x3 phase kernels) pushed through the CPU emulation of the kernels' data flow
