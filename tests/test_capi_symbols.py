@@ -50,3 +50,29 @@ def test_struct_sizes_match_header():
     # gfpp_model is 512 x uint64
     assert ctypes.sizeof(_capi.Model) == 4096
     assert ctypes.sizeof(_capi.GridDesc) == 48
+
+
+def test_round2_entry_points_validate_before_any_cuda_call():
+    """SR / torso-SR / training-side entry points (gfpp.h sections C and D): null pointers, unsupported shapes, foreign handles and
+    short buffers are reported through the status code + gfpp_last_error(), without a GPU."""
+    L = _capi.lib()
+    P = ctypes.c_void_p
+    assert L.gfpp_sr_packed_bytes() > 900_000 and L.gfpp_sr_workspace_bytes(1, 256) > 60_000_000
+    assert L.gfpp_torso_sr_packed_bytes() > 40_000 and L.gfpp_torso_sr_workspace_bytes(8) >= 8 * 96 * 4
+    assert L.gfpp_march_rays_train_scratch_bytes(4096) >= 8
+    assert L.gfpp_sr_pack(None, None, 0, None, None) == -1 and b"null" in L.gfpp_last_error()
+    d, m = _capi.SrDesc(), _capi.SrModel()
+    assert L.gfpp_sr_pack(ctypes.byref(d), P(4096), 10, ctypes.byref(m), None) == -1            # null weights
+    assert L.gfpp_sr_forward(ctypes.byref(m), 1, 256, P(4096), None, 0, P(4096), 0, P(4096), 1 << 30, None) == -1   # handle never packed
+    assert b"gfpp_sr_pack" in L.gfpp_last_error()
+    td, tm, tf = _capi.TorsoSrDesc(), _capi.TorsoSrModel(), _capi.TorsoSrFrames()
+    assert L.gfpp_torso_sr_pack(ctypes.byref(td), P(4096), 1 << 20, ctypes.byref(tm), None) == -1
+    assert L.gfpp_torso_sr_composite(ctypes.byref(tm), ctypes.byref(tf), P(4096), None, None, None, None, P(4096), 1 << 20, None) == -1
+    assert b"gfpp_torso_sr_pack" in L.gfpp_last_error()
+    assert L.gfpp_march_rays_train(*([None] * 3), 1.0, 0.0, 16, 8, 1, 128, 64, *([None] * 9), 0, None) == -1
+    assert L.gfpp_composite_rays_train_forward(*([None] * 5), 0, 0, 1e-4, *([None] * 5)) == -1
+    assert L.gfpp_grid_encode_backward(P(8), P(8), P(8), P(8), P(8), 4, 3, 4, 16, 0.5, 16, None, None, 1, 0, 0, None) == -4      # C must be 2
+    assert L.gfpp_grid_encode_backward(P(8), P(8), P(8), P(8), P(8), 4, 3, 2, 16, 0.5, 16, P(8), None, 1, 0, 0, None) == -1     # dy_dx without grad_inputs
+    assert L.gfpp_packbits(P(8), 4, 0.5, P(8), None) == -1 and b"aligned" in L.gfpp_last_error()
+    assert L.gfpp_morton3D_dilation(P(16), 9, 128, P(16), None) == -1
+    assert ctypes.sizeof(_capi.SrModel) == 256 and ctypes.sizeof(_capi.TorsoSrModel) == 1024
