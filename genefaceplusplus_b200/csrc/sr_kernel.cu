@@ -316,8 +316,10 @@ __global__ void __launch_bounds__(NT, LAYER == 1 ? 1 : 2) k_sr_conv(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// block0.conv0: 3 -> 128 channels.  One task = two horizontally adjacent pixels x 16 output channels (the weights of a
-// k are read once from shared memory for both pixels); eight consecutive threads write the 256 contiguous bytes of a pixel.
+// block0.conv0: 3 -> 128 channels.  One task = two horizontally adjacent pixels x 16 output channels.  A warp takes ONE group of 16
+// channels for 32 neighbouring pixel pairs, so every shared-memory weight read is a broadcast (one 16-byte wavefront instead of eight:
+// the first version, which spread the eight channel groups over the lanes, was bound by exactly those reads -- ncu: L1TEX 96 %,
+// short-scoreboard 8.4 per issue); the eight warps of a CTA cover the eight channel groups of the same 64 pixels.
 __global__ void __launch_bounds__(256) k_sr_conv_in(const __grid_constant__ SrConvInArgs a) {
     __shared__ __align__(16) float sw[27 * 128];
     __shared__ float sb[128];
@@ -325,10 +327,10 @@ __global__ void __launch_bounds__(256) k_sr_conv_in(const __grid_constant__ SrCo
     if (threadIdx.x < 128) sb[threadIdx.x] = a.bias[threadIdx.x];
     __syncthreads();
     const int Wh = a.W / 2;
-    const long long n_tasks = (long long)a.F * a.H * Wh * 8;
-    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < n_tasks; t += (long long)gridDim.x * 256) {
-        const int cg = (int)(t & 7);
-        const long long pp = t >> 3;
+    const long long n_groups = (long long)a.F * a.H * Wh / 32;       // groups of 32 pixel pairs (W % 64 == 0)
+    const int cg = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const long long pp = grp * 32 + lane;
         const int xh = (int)(pp % Wh);
         const long long r = pp / Wh;
         const int y = (int)(r % a.H), f = (int)(r / a.H);
@@ -386,8 +388,8 @@ __global__ void __launch_bounds__(256) k_sr_conv_in(const __grid_constant__ SrCo
 }
 
 cudaError_t launch_sr_conv_in(const SrConvInArgs &a, cudaStream_t st) {
-    if (a.W % 2) return cudaErrorInvalidValue;
-    const uint64_t n_tasks = (uint64_t)a.F * a.H * (a.W / 2) * 8;
+    if (a.W % 64) return cudaErrorInvalidValue;
+    const uint64_t n_tasks = (uint64_t)a.F * a.H * (a.W / 2) * 8;   // one CTA iteration = 32 pixel pairs x 8 channel groups
     k_sr_conv_in<<<grid_for(n_tasks, 256), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
