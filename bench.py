@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-other-mode", action="store_true", help="skip measuring the other precision mode (fp16 <-> robust) beside the headline one")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own CUDA kernels (oracle/_ref) beside ours")
     ap.add_argument("--no-sr-variants", action="store_true", help="skip the short measurement of the SR-checkpoint paths (SURVEY 8(f) rank 3)")
+    ap.add_argument("--no-train-ops", action="store_true", help="skip timing the training-side native ops beside the reference's kernels (SURVEY 8(f) rank 4)")
     ap.add_argument("--precision", default=os.environ.get("GFPP_BENCH_PRECISION", DEFAULT_PRECISION), choices=["fp32", "fp16", "bf16x3", "bf16", "robust"],
                     help="arithmetic of the head MLP GEMMs (marching/gather/compositing are fp32 in every mode)")
     return ap.parse_args()
@@ -522,6 +523,16 @@ def _main(args, out):
             sr = {"config": "256x256 NeRF (fp16 tcgen05) -> 512x512, 32-frame clips, resident inputs, CUDA events, median of 3", "results": sr_bench.measure(32, 3)}
         except Exception as ex:   # an extra measurement must never take the bench down
             sr = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+    train = None
+    if rank == 0 and world == 1 and not args.no_train_ops:
+        # SURVEY 8(f) rank 4, measured in the same run: libgfpp's training-side ops beside the reference's own training kernels
+        # (oracle/_ref) on the same inputs (tools/train_bench.py).  Last measurement of the run: nothing depends on it.
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import train_bench
+            train = train_bench.measure(256, 5)
+        except Exception as ex:   # an extra measurement must never take the bench down
+            train = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     if rank == 0:
         line = {"metric": metric_name(args), "value": fps,
                 "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -538,7 +549,7 @@ def _main(args, out):
                                                   "region), uint8 [T,H,W,3] frames written by the epilogue kernel" +
                                                   (", all-gather of the uint8 clip, D2H of the whole clip on rank 0" if world > 1 else ", D2H of the clip")},
                 "gpu_launches": timed_launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "gpu_reference": gpu_ref,
-                "other_mode": other, "sr_variants": sr}
+                "other_mode": other, "sr_variants": sr, "train_ops": train}
         print(json.dumps(line), file=out)
     if world > 1:
         dist.destroy_process_group()
