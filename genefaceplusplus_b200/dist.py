@@ -91,18 +91,23 @@ def to_uint8(rgb: torch.Tensor) -> torch.Tensor:
 
 
 def render_clip_sharded(model, poses_c2w, intrinsics, H, W, cond_seq, *, bg_color=None, bg_coords=None, T_thresh=1e-2,
-                        frames_per_call=64, as_uint8=False, gather=True, group=None):
+                        frames_per_call=64, as_uint8=False, gather=True, group=None, eye_area_percent=None, lm68_seq=None, **render_kw):
     """Render this rank's block of the clip with `model.render_clip` and all-gather the result.
 
-    `cond_seq` is the FULL conditioning sequence [T,1,C] on every rank (the +-2-frame smoothing window needs
-    its halo; it is tiny), so conditioning features at block edges equal the single-GPU ones."""
+    `cond_seq` (and `eye_area_percent` [T] for the blink-conditioned models) is the FULL sequence on every rank -- the +-2-frame
+    smoothing window needs its halo; it is tiny -- so conditioning features at block edges equal the single-GPU ones.  Per-frame
+    inputs of the SR models (`lm68_seq` [T,136]) are sliced to the rank's block; `render_kw` goes to `render_clip` unchanged
+    (`sr_noise_mode=...`).  Works for all four model classes: [T,N,3] frames for the plain models, [T,3,512,512] for the SR ones."""
     T = poses_c2w.shape[0]
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     s, e = frame_block(T, rank, world)
-    cond_feat = model.cal_cond_feat_clip(cond_seq.to(model.density_bitfield.device))[s:e]
-    local = model.render_clip(poses_c2w[s:e], intrinsics, H, W, cond_feat=cond_feat, bg_color=bg_color, bg_coords=bg_coords,
-                              T_thresh=T_thresh, frames_per_call=frames_per_call)
+    cond_seq = cond_seq.to(model.density_bitfield.device)
+    cond_feat = (model.cal_cond_feat_clip(cond_seq) if eye_area_percent is None else model.cal_cond_feat_clip(cond_seq, eye_area_percent=eye_area_percent))[s:e]
+    kw = dict(cond_feat=cond_feat, bg_color=bg_color, bg_coords=bg_coords, T_thresh=T_thresh, frames_per_call=frames_per_call, **render_kw)
+    if lm68_seq is not None:
+        kw["lm68_seq"] = lm68_seq[s:e]
+    local = model.render_clip(poses_c2w[s:e], intrinsics, H, W, **kw)
     if as_uint8:
         local = to_uint8(local)
     return gather_frames(local, T, group) if gather else local

@@ -825,7 +825,7 @@ class RADNeRFTorsowithSR(RADNeRF):
 
     @torch.no_grad()
     def render_clip(self, poses_c2w, intrinsics, H=256, W=256, cond_seq=None, bg_color=None, bg_coords=None, lm68_seq=None,
-                    eye_area_percent=None, dt_gamma=None, max_steps=None, T_thresh=1e-2, sr_noise_mode="random", **unused):
+                    eye_area_percent=None, dt_gamma=None, max_steps=None, T_thresh=1e-2, sr_noise_mode="random", cond_feat=None, **unused):
         """Clip convenience for the torso-SR model: frame-by-frame `render()` (the torso field of this variant is still
         host-side), returning the clamped 512x512 frames [T,3,512,512].  poses_c2w [T,4,4] (c2w, dataset.poses), cond_seq
         [T,1,C], lm68_seq [T,136], eye_area_percent [T] or None."""
@@ -840,8 +840,9 @@ class RADNeRFTorsowithSR(RADNeRF):
         if self.torso_backend == "native" and self.sr_net.backend == "native":
             # everything in libgfpp, chunk by chunk: head field (rays generated in-kernel, background 0 => premultiplied colour),
             # torso-SR field + composite, SR head; no per-frame host work
-            fpc = int(unused.get("frames_per_call", 8))
-            cond_feat = self.cal_cond_feat_clip(cond_seq.to(dev), eye_area_percent=eye_area_percent)
+            fpc = min(8, int(unused.get("frames_per_call", 8)))     # the SR workspace is 68 MB per frame
+            if cond_feat is None:                                   # [T,64] precomputed (sharded clips: dist.render_clip_sharded) or from the sequence
+                cond_feat = self.cal_cond_feat_clip(cond_seq.to(dev), eye_area_percent=eye_area_percent)
             poses_c2w = poses_c2w.to(dev, torch.float32)
             zero_bg = torch.zeros(R * R, 3, device=dev)
             with torch.autocast(dev.type, enabled=False):
@@ -854,6 +855,8 @@ class RADNeRFTorsowithSR(RADNeRF):
                                                      want_maps=False)
                     self.sr_net.forward_native(tr["rgb_map"], noise_mode=sr_noise_mode, clamp=True, out=out[s:e], frames_per_call=fpc)
             return out
+        if cond_seq is None:
+            raise ValueError("the frame-by-frame host path of the torso-SR clip needs cond_seq (cond_feat is only taken by the all-native path)")
         for t in range(T):
             rays_o, rays_d = get_rays(poses_c2w[t].cpu(), intrinsics, H, W)
             res = self.render(rays_o.to(dev), rays_d.to(dev), cond_window(cond_seq, t, self.smo_win_size).to(dev), bg_coords,

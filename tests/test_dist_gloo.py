@@ -37,6 +37,20 @@ class _FakeRenderer:
         return t.view(-1, 1, 1).expand(-1, H * W, 3).contiguous()
 
 
+class _FakeSRRenderer(_FakeRenderer):
+    """SR-model shape of the clip API: blink-conditioned features from the FULL sequence, per-frame landmarks sliced to the block,
+    [t,3,4,4] frames out, extra keyword arguments passed through."""
+
+    def cal_cond_feat_clip(self, cond_seq, eye_area_percent=None):
+        assert eye_area_percent is not None and eye_area_percent.shape[0] == cond_seq.shape[0]
+        return cond_seq.reshape(cond_seq.shape[0], -1)[:, :4].clone() + eye_area_percent.view(-1, 1)
+
+    def render_clip(self, poses, intrinsics, H, W, cond_feat=None, lm68_seq=None, sr_noise_mode=None, **kw):
+        t = poses[:, 0, 3]
+        assert torch.allclose(cond_feat[:, 0], t + 0.25) and torch.allclose(lm68_seq[:, 0], t) and sr_noise_mode == "const"
+        return t.view(-1, 1, 1, 1).expand(-1, 3, 4, 4).contiguous()
+
+
 def _worker(rank, world, port, T, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -45,6 +59,10 @@ def _worker(rank, world, port, T, q):
     cond = torch.arange(T, dtype=torch.float32).view(T, 1, 1).expand(T, 1, 8).contiguous()
     out = gdist.render_clip_sharded(_FakeRenderer(), poses, (1, 1, 0, 0), 2, 2, cond, as_uint8=False)
     u8 = gdist.gather_frames(gdist.to_uint8(torch.full((gdist.frame_block(T, rank, world)[1] - gdist.frame_block(T, rank, world)[0], 4, 3), 0.5)), T)
+    lm = torch.arange(T, dtype=torch.float32).view(T, 1).expand(T, 136).contiguous()
+    sr = gdist.render_clip_sharded(_FakeSRRenderer(), poses, (1, 1, 0, 0), 2, 2, cond, eye_area_percent=torch.full((T,), 0.25), lm68_seq=lm,
+                                   sr_noise_mode="const")
+    assert sr.shape == (T, 3, 4, 4) and sr[:, 0, 0, 0].tolist() == [float(t) for t in range(T)]     # SR-model clips shard the same way
     q.put((rank, out[:, 0, 0].tolist(), tuple(u8.shape), int(u8.max())))
     dist.destroy_process_group()
 
