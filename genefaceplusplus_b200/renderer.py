@@ -599,9 +599,11 @@ class RADNeRFTorsowithSR(RADNeRF):
     `torso_deform_net.*`, `torso_canonicial_net.*`, `sr_net.*`, blink modules) and `render(..., lm68=, eye_area_percent=,
     upscale_torso=)` result dict.  The head NeRF runs in libgfpp's fused kernels at 256x256; this variant's torso field --
     2-D position (42) + code (8) + freq-encoded jaw landmarks (126) [+ a per-pixel 4->16->32->16 encoding of the head colour and
-    alpha] -> deform 64-64-2 -> tiled 2-D grid -> canonical 32-32-4 -- the three-way composite and the SR head are host-side
-    PyTorch on top of libgfpp's per-op encoder kernels for now (first correct path; the fused `k_epilogue` only knows the
-    non-SR torso field).  Pinned on CPU against tests/golden/torso_sr256.npz with the encoders injected from the checker."""
+    alpha] -> deform 64-64-2 -> tiled 2-D grid -> canonical 32-32-4 -- and the three-way composite run in libgfpp's `k_torso_sr`
+    (csrc/torso_sr_kernel.cu, `torso_backend = "native"`), the SR head in libgfpp's tcgen05 convolution kernels (superres.py).
+    `torso_backend = "torch"` keeps the first correct path -- the field as host-side PyTorch over libgfpp's per-op encoder kernels --
+    as the A/B reference of the kernel; it is also what the CPU test drives with the encoders injected from the checker
+    (tests/golden/torso_sr256.npz).  On the B200 both are pinned against the reference's own render() golden."""
     has_torso = False            # what gets packed for libgfpp is the head field only
     forwards_eye_area = True     # radnerf_torso_sr.py:136
     sr_input_resolution = 256
@@ -826,9 +828,10 @@ class RADNeRFTorsowithSR(RADNeRF):
     @torch.no_grad()
     def render_clip(self, poses_c2w, intrinsics, H=256, W=256, cond_seq=None, bg_color=None, bg_coords=None, lm68_seq=None,
                     eye_area_percent=None, dt_gamma=None, max_steps=None, T_thresh=1e-2, sr_noise_mode="random", cond_feat=None, **unused):
-        """Clip convenience for the torso-SR model: frame-by-frame `render()` (the torso field of this variant is still
-        host-side), returning the clamped 512x512 frames [T,3,512,512].  poses_c2w [T,4,4] (c2w, dataset.poses), cond_seq
-        [T,1,C], lm68_seq [T,136], eye_area_percent [T] or None."""
+        """Clip API of the torso-SR model -> the clamped 512x512 frames [T,3,512,512].  With the native backends (the default) every
+        stage runs in libgfpp chunk by chunk -- head field with rays generated in-kernel, torso-SR field + composite, SR head -- with
+        no per-frame host work; with a "torch" backend it falls back to frame-by-frame `render()`.  poses_c2w [T,4,4] (c2w,
+        dataset.poses), cond_seq [T,1,C] (or cond_feat [T,64] precomputed), lm68_seq [T,136], eye_area_percent [T] or None."""
         from .scene import cond_window, convert_poses, get_rays
         R = self.sr_input_resolution
         if (H, W) != (R, R):
