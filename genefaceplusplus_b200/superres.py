@@ -176,15 +176,26 @@ class Superresolution(nn.Module):
           conv1_w   [64,576]    block1.conv1, k = (ky*3+kx)*64 + ci
           bias[4], rgb_w[2] ([3,C]: toRGB weight * style / sqrt(C)), rgb_b[2]
         """
+        # computed on the host from CPU copies of the (small) parameters -- a few hundred tiny tensor ops that would otherwise be a
+        # few hundred kernel launches per (re)pack -- and moved to the parameters' device at the end
         dev = self.block0.conv0.weight.device
-        w = torch.ones(self.w_dim, dtype=torch.float32, device=dev)
+        w = torch.ones(self.w_dim, dtype=torch.float32)
         b0, b1 = self.block0, self.block1
-        k00, k01 = b0.conv0.modulated_weight(w).float(), b0.conv1.modulated_weight(w).float()
-        k10, k11 = b1.conv0.modulated_weight(w).double(), b1.conv1.modulated_weight(w).float()
-        f1 = b1.conv0.resample_filter.double().sum(dim=0)        # separable: rows of outer(f,f)/64 sum to f/8
+
+        def c(t):
+            return t.detach().float().cpu()
+
+        def mod_w(layer):     # _ModConv.modulated_weight on the CPU copies
+            s_ = torch.addmv(c(layer.affine.bias), c(layer.affine.weight) * layer.affine.weight_gain, w)
+            k = c(layer.weight) * s_.view(1, -1, 1, 1)
+            return k * (k.square().sum(dim=[1, 2, 3]) + 1e-8).rsqrt().view(-1, 1, 1, 1)
+
+        k00, k01 = mod_w(b0.conv0), mod_w(b0.conv1)
+        k10, k11 = mod_w(b1.conv0).double(), mod_w(b1.conv1)
+        f1 = c(b1.conv0.resample_filter).double().sum(dim=0)     # separable: rows of outer(f,f)/64 sum to f/8
         f1 = f1 / f1.sum() * 2.0                                 # [1,3,3,1]/8 * 2
         O, I = k10.shape[:2]
-        K = torch.zeros(2, 2, O, I, 3, 3, dtype=torch.float64, device=dev)
+        K = torch.zeros(2, 2, O, I, 3, 3, dtype=torch.float64)
         for p in range(2):
             for ty in range(4):
                 for ay in range(3):
@@ -200,20 +211,22 @@ class Superresolution(nn.Module):
                                 K[p, q, :, :, oy, ox] += f1[ty] * f1[tx] * k10[:, :, ay, ax]
 
         def rgb(t):
-            s = t.affine(w) * t.weight_gain
-            return (t.weight[:, :, 0, 0] * s.view(1, -1)).float().contiguous(), t.bias.detach().float().contiguous()
+            s_ = torch.addmv(c(t.affine.bias), c(t.affine.weight) * t.affine.weight_gain, w) * t.weight_gain
+            return (c(t.weight)[:, :, 0, 0] * s_.view(1, -1)).contiguous(), c(t.bias).contiguous()
 
         r0w, r0b = rgb(b0.torgb)
         r1w, r1b = rgb(b1.torgb)
-        return {
+        fw = {
             "conv_in_w": k00.permute(2, 3, 1, 0).reshape(27, 128).contiguous(),
             "conv0_w": k01.permute(0, 2, 3, 1).reshape(128, 9 * 128).contiguous(),
             "up_w": K.permute(0, 1, 2, 4, 5, 3).reshape(4 * O, 9 * I).float().contiguous(),
             "conv1_w": k11.permute(0, 2, 3, 1).reshape(64, 9 * 64).contiguous(),
-            "bias": [b0.conv0.bias.detach().float().contiguous(), b0.conv1.bias.detach().float().contiguous(),
-                     b1.conv0.bias.detach().float().contiguous(), b1.conv1.bias.detach().float().contiguous()],
+            "bias": [c(b0.conv0.bias).contiguous(), c(b0.conv1.bias).contiguous(), c(b1.conv0.bias).contiguous(), c(b1.conv1.bias).contiguous()],
             "rgb_w": [r0w, r1w], "rgb_b": [r0b, r1b],
         }
+        if dev.type == "cpu":
+            return fw
+        return {k: ([t.to(dev) for t in v] if isinstance(v, list) else v.to(dev)) for k, v in fw.items()}
 
     def _layers(self):
         return (self.block0.conv0, self.block0.conv1, self.block1.conv0, self.block1.conv1)
@@ -242,7 +255,7 @@ class Superresolution(nn.Module):
             with torch.cuda.device(dev):
                 _capi.check(L.gfpp_sr_pack(ctypes.byref(d), _capi.c_void_p(packed.data_ptr() + off), packed.numel() - off,
                                            ctypes.byref(model), _capi.stream_ptr(dev)), "gfpp_sr_pack")
-            strengths = [float(l.noise_strength) for l in self._layers()]       # one sync per (re)pack
+            strengths = [float(l.noise_strength.detach()) for l in self._layers()]       # one sync per (re)pack
             st = {"key": key, "packed": packed, "model": model, "fw": fw, "strengths": strengths, "ws": None}
             self.__dict__["_native"] = st
         return st
